@@ -1,0 +1,80 @@
+// Laplace CDF -> 16-bit integer CDF, evaluated identically on the device (encoder-side
+// bounds kernel) and on the host (range decoder's per-symbol search).
+//
+// Follows src/real_life/bitstream.py:127-154 (get_y_cdf: Laplace(0, sigma/sqrt(2)).cdf on the
+// grid idx = i - 256.5, i in [0, 514)) and torchac's float->int16 normalisation as called at
+// bitstream.py:281,454 (round(cdf * (2^16 - 513)) + i, mod 2^16).  Every step is the fp32
+// operation torch performs, in the same order, except expm1f: torch's vectorised expm1f is
+// not reproducible across devices, so it is replaced by a double-precision evaluation built
+// only from IEEE add/mul/fma (bit-identical on x86-64 and sm_100a) and rounded once to fp32.
+// Encoder and decoder therefore always agree, on any mix of host and device.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDA_ARCH__)
+#define AIVC_HD __host__ __device__ __forceinline__
+#define AIVC_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define AIVC_MUL(a, b) __dmul_rn((a), (b))
+#define AIVC_SUB(a, b) __dsub_rn((a), (b))
+#define AIVC_FDIV(a, b) __fdiv_rn((a), (b))
+#define AIVC_FMULF(a, b) __fmul_rn((a), (b))
+#define AIVC_FSUBF(a, b) __fsub_rn((a), (b))
+#define AIVC_FADDF(a, b) __fadd_rn((a), (b))
+#else
+#if defined(__CUDACC__)
+#define AIVC_HD __host__ __device__ inline
+#else
+#define AIVC_HD static inline
+#endif
+// host: translation units including this header are built with -ffp-contract=off
+#define AIVC_FMA(a, b, c) fma((a), (b), (c))
+#define AIVC_MUL(a, b) ((a) * (b))
+#define AIVC_SUB(a, b) ((a) - (b))
+#define AIVC_FDIV(a, b) ((a) / (b))
+#define AIVC_FMULF(a, b) ((a) * (b))
+#define AIVC_FSUBF(a, b) ((a) - (b))
+#define AIVC_FADDF(a, b) ((a) + (b))
+#endif
+
+#define AIVC_AC_MAX_VAL 256
+#define AIVC_AC_LP 514            /* 2*AC_MAX_VAL + 2, bitstream.py:134 */
+#define AIVC_CDF_SCALE 65023.0f   /* 2^16 - (Lp - 1) */
+#define AIVC_SQRT2_F 1.41421354f  /* fp32 sqrt(2), as torch.sqrt(torch.tensor([2.0])) */
+
+// expm1(x) for x <= 0, |error| ~1e-16: k = rint(x*log2e), r = x - k*ln2, Taylor(12) for e^r - 1.
+AIVC_HD double aivc_expm1_neg(double x) {
+    if (x <= -20.0) return -1.0;     // e^x < 2^-28: the fp32 result is exactly -1
+    const double k = rint(AIVC_MUL(x, 1.4426950408889634));
+    double r = AIVC_FMA(-k, 6.93147180369123816490e-01, x);
+    r = AIVC_FMA(-k, 1.90821492927058770002e-10, r);
+    double e = 2.08767569878680989792e-09;                  // 1/12!
+    e = AIVC_FMA(e, r, 2.50521083854417187751e-08);         // 1/11!
+    e = AIVC_FMA(e, r, 2.75573192239858906526e-07);         // 1/10!
+    e = AIVC_FMA(e, r, 2.75573192239858906526e-06);         // 1/9!
+    e = AIVC_FMA(e, r, 2.48015873015873015873e-05);         // 1/8!
+    e = AIVC_FMA(e, r, 1.98412698412698412698e-04);         // 1/7!
+    e = AIVC_FMA(e, r, 1.38888888888888888889e-03);         // 1/6!
+    e = AIVC_FMA(e, r, 8.33333333333333333333e-03);         // 1/5!
+    e = AIVC_FMA(e, r, 4.16666666666666666667e-02);         // 1/4!
+    e = AIVC_FMA(e, r, 1.66666666666666666667e-01);         // 1/3!
+    e = AIVC_FMA(e, r, 0.5);                                // 1/2!
+    const double p = AIVC_FMA(AIVC_MUL(e, r), r, r);        // e^r - 1
+    union { uint64_t u; double d; } two_k;
+    two_k.u = (uint64_t)(1023 + (int)k) << 52;              // 2^k, k in [-29, 0]
+    return AIVC_FMA(two_k.d, p, AIVC_SUB(two_k.d, 1.0));
+}
+
+// b = sigma / sqrt(2) in fp32 (bitstream.py:141)
+AIVC_HD float aivc_laplace_scale(float sigma) { return AIVC_FDIV(sigma, AIVC_SQRT2_F); }
+
+// 16-bit integer CDF entry i (0 <= i < 514) of the Laplace with scale b.
+AIVC_HD uint32_t aivc_laplace_cdf_int(float b, int i) {
+    const float t = (float)i - 256.5f;                       // exact
+    const float x = AIVC_FDIV(-fabsf(t), b);
+    const float e = (float)aivc_expm1_neg((double)x);
+    const float hs = t < 0.f ? -0.5f : 0.5f;                 // 0.5 * sign(t); t is never 0
+    const float cdf = AIVC_FSUBF(0.5f, AIVC_FMULF(hs, e));
+    const float scaled = rintf(AIVC_FMULF(cdf, AIVC_CDF_SCALE));
+    return ((uint32_t)(int32_t)scaled + (uint32_t)i) & 0xFFFFu;
+}
