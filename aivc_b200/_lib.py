@@ -1,0 +1,103 @@
+"""ctypes binding of libaivc_b200.so (the C ABI declared in include/aivc_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C aivc_b200/csrc``).
+If it is missing the product path fails loudly: there is no fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libaivc_b200.so')
+
+F32, BF16 = 0, 1
+ACT = {'no': 0, 'none': 0, 'leaky_relu': 1, 'relu': 2, 'sigmoid': 3, 'gdn': 4, 'gdn_inverse': 5}
+POST = {'none': 0, 'leaky_relu': 1, 'relu': 2, 'round_clamp': 3}
+ENGINE_SIMT, ENGINE_TC = 0, 1
+
+
+class FMap(C.Structure):
+    _fields_ = [('data', C.c_void_p), ('h', C.c_int32), ('w', C.c_int32), ('c', C.c_int32),
+                ('c_off', C.c_int32), ('c_stride', C.c_int32), ('pad', C.c_int32),
+                ('pitch', C.c_int32), ('rows', C.c_int32), ('dtype', C.c_int32), ('_r', C.c_int32)]
+
+
+class ConvOp(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('k', C.c_int32), ('stride', C.c_int32), ('engine', C.c_int32),
+                ('inp', FMap), ('out', FMap),
+                ('weight', C.c_void_p), ('bias', C.c_void_p),
+                ('act', C.c_int32), ('post', C.c_int32),
+                ('gdn_beta', C.c_void_p), ('gdn_gamma', C.c_void_p),
+                ('residual', FMap), ('gate', FMap),
+                ('out_scale', C.c_void_p), ('scratch', C.c_void_p),
+                ('act_channels', C.c_int32), ('_r', C.c_int32)]
+
+
+_lib = None
+
+_SIGS = {
+    # name: (restype, argtypes)
+    'aivc_abi_version': (C.c_int, []),
+    'aivc_last_error': (C.c_char_p, []),
+    'aivc_pack_conv_weight': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 6),
+    'aivc_conv2d_fused': (C.c_int, [C.POINTER(ConvOp), C.c_void_p]),
+    'aivc_conv2d_fused_seq': (C.c_int, [C.POINTER(ConvOp), C.c_int, C.c_void_p]),
+    'aivc_nchw_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+    'aivc_fmap_to_nchw': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
+    'aivc_fill_border': (C.c_int, [C.POINTER(FMap), C.c_void_p]),
+    'aivc_yuv420_to_fmap': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(FMap),
+                                      C.c_void_p]),
+    'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int] + [C.POINTER(FMap)] * 2 + [C.c_void_p]),
+    'aivc_warp_blend_nchw': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    'aivc_finalize_frame': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+    'aivc_mu_sigma_nchw': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'aivc_quantize_latent': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+    'aivc_laplace_scale': (C.c_int, [C.POINTER(FMap), C.c_int, C.c_void_p, C.c_void_p]),
+    'aivc_dequantize_latent': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p, C.POINTER(FMap),
+                                         C.c_void_p]),
+    'aivc_fmap_to_i16': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
+    'aivc_i16_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+    'aivc_rc_bound': (C.c_size_t, [C.c_size_t]),
+    'aivc_rc_encode_bounds': (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]),
+    'aivc_rc_encode_table': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p,
+                                       C.c_size_t, C.POINTER(C.c_size_t)]),
+    'aivc_rc_decode_table': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t,
+                                       C.c_void_p]),
+    'aivc_rc_decode_laplace': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    'aivc_laplace_cdf_int_host': (C.c_uint32, [C.c_float, C.c_int]),
+    'aivc_sigma_from_logvar_host': (C.c_float, [C.c_float]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load (once) and return the library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'aivc_b200: %s is missing -- build it with `python -c "import __graft_entry__ as g; '
+                'g.build()"` or `make -C aivc_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.aivc_abi_version() != 1:
+            raise RuntimeError('aivc_b200: ABI version mismatch')
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('aivc_b200: ' + lib().aivc_last_error().decode())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

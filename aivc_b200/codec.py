@@ -1,0 +1,278 @@
+"""Per-frame AIVC encoder / decoder on one B200.
+
+Data flow of one inter frame (I frames skip the MOFNet half), all on one CUDA stream:
+
+  planes (u8) --yuv420_to_fmap--> mof_in [code|prev|next] --g_a--> y --h_a--> z^ --h_s--> (mu, log var)
+                                                                   \\--quantize_latent--> q, CDF bounds, y^
+        g_a_ref(prev,next) --------------------------------> [y^ | shortcut] --g_s--> alpha,beta,v_prev,v_next
+  warp_blend(prev, next) --> pred (-> codec_in [code|pred]), skip
+  CodecNet: same chain on codec_in, shortcut = g_a_ref(pred)
+  finalize_frame(codec_out + skip) --> 8-bit 4:2:0 planes (the reference for later frames)
+
+It follows real_life/decode.py:455-898 (decoder) and its mirror for the encoder
+(SURVEY.md 8a-19); entropy coding is handed to the host range coder (entropy.py) through
+int16 symbols + 16-bit CDF bounds (encoder) or fp32 Laplace scales (decoder).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, entropy
+from ._lib import F32
+from .gop import FRAME_I, FRAME_P, FRAME_B, coding_order
+from .plan import Plan, Buffer, Config
+
+
+def _ceil_half(v, n):
+    for _ in range(n):
+        v = (v + 1) // 2
+    return v
+
+
+def latent_dims(h, w):
+    return (_ceil_half(h, 4), _ceil_half(w, 4)), (_ceil_half(h, 6), _ceil_half(w, 6))
+
+
+def _gain_of(net, frame_type):
+    if not net.flag_gain_p_b or frame_type == FRAME_I:
+        return net.gain_I
+    return net.gain_P if frame_type == FRAME_P else net.gain_B
+
+
+def _gain_vec(gm, idx_rate, mode):
+    if hasattr(gm, 'gain_vector'):
+        return gm.gain_vector(idx_rate, mode).reshape(-1)
+    return gm.interpolate_gain_vector(idx_rate, mode=mode).detach().reshape(-1)
+
+
+class CondNetEngine:
+    """Kernel plans and staging buffers of one ConditionalNet at a fixed frame size."""
+
+    def __init__(self, net, h, w, in_buf, ref_off, ref_c, device, cfg, idx_rate=0.):
+        self.net, self.device = net, device
+        cy, cz, csc = net.nb_ft_y, net.nb_ft_z, net.out_c_shortcut_y
+        self.cy, self.cz, self.csc = cy, cz, csc
+        (hy, wy), (hz, wz) = latent_dims(h, w)
+        self.dims_y, self.dims_z = (hy, wy), (hz, wz)
+        exact = Config(precision='fp32')           # hyperprior: exact engine (sigma steers the coder)
+        self.g_s = Plan(net.g_s, hy, wy, cy + csc, device, cfg)
+        self.gs_in = self.g_s.src.buf
+        self.has_ref = getattr(net, 'g_a_ref', None) is not None
+        self.h_s = Plan(net.h_s, hz, wz, cz, device, exact)
+        if getattr(net, 'g_a', None) is not None:        # a decoder-only model has no analysis side
+            self.g_a = Plan(net.g_a, h, w, in_buf.c, device, cfg, src_buf=in_buf,
+                            out_scale=torch.ones(cy))
+            self.h_a = Plan(net.h_a, hy, wy, cy, device, exact, src_buf=self.g_a.dst.buf,
+                            dst_into=(self.h_s.src.buf, 0), out_post='round_clamp')
+        if self.has_ref:
+            self.g_a_ref = Plan(net.g_a_ref, h, w, ref_c, device, cfg, src_buf=in_buf,
+                                src_c_off=ref_off, dst_into=(self.gs_in, cy))
+        self.table = entropy.z_table_u16(net.pdf_z)
+        self.gains = {}
+        for ft in (FRAME_I, FRAME_P, FRAME_B):
+            gm = _gain_of(net, ft)
+            self.gains[ft] = (_gain_vec(gm, idx_rate, 'enc').float().to(device).contiguous(),
+                              _gain_vec(gm, idx_rate, 'dec').float().to(device).contiguous())
+        n_y, n_z = cy * hy * wy, cz * hz * wz
+        dev = dict(device=device)
+        self.q_dev = torch.empty(n_y, dtype=torch.int16, **dev)
+        self.bounds_dev = torch.empty(n_y, dtype=torch.int32, **dev)
+        self.nz_dev = torch.zeros(cy, dtype=torch.int32, **dev)
+        self.z_dev = torch.empty(n_z, dtype=torch.int16, **dev)
+        self.b_dev = torch.empty(n_y, dtype=torch.float32, **dev)
+        pin = dict(pin_memory=True)
+        self.q_host = torch.empty(n_y, dtype=torch.int16, **pin)
+        self.bounds_host = torch.empty(n_y, dtype=torch.int32, **pin)
+        self.nz_host = torch.empty(cy, dtype=torch.int32, **pin)
+        self.z_host = torch.empty(n_z, dtype=torch.int16, **pin)
+        self.b_host = torch.empty(n_y, dtype=torch.float32, **pin)
+        self.last = {}
+
+    def _yhat_view(self):
+        return self.gs_in.view(0, self.cy)
+
+    def _shortcut(self, use):
+        if use and self.has_ref:
+            self.g_a_ref.run()
+        else:   # zeros (decode.py:891-892), border included
+            full = self.gs_in.t.view(self.gs_in.rows, self.gs_in.pitch, self.gs_in.c)
+            full[:, :, self.cy:].zero_()
+
+    def encode(self, frame_type, use_shortcut, first_of_i_frame=False):
+        """Runs analysis + synthesis; returns the two bitstream sections. The synthesis
+        output stays in ``self.g_s.dst``."""
+        L, st = _lib.lib(), _lib.stream_ptr()
+        enc_gain, dec_gain = self.gains[frame_type]
+        self.g_a.ops[len(self.g_a.ops) - 1].out_scale = enc_gain.data_ptr()
+        self.g_a.run()
+        self.h_a.run()
+        zf = self.h_s.in_fmap
+        _lib.check(L.aivc_fmap_to_i16(C.byref(zf), self.z_dev.data_ptr(), st))
+        self.z_host.copy_(self.z_dev, non_blocking=True)
+        self.h_s.run()
+        self.nz_dev.zero_()
+        yf, hsf, yh = self.g_a.out_fmap, self.h_s.out_fmap, self._yhat_view()
+        _lib.check(L.aivc_quantize_latent(C.byref(yf), C.byref(hsf), dec_gain.data_ptr(),
+                                          self.q_dev.data_ptr(), self.bounds_dev.data_ptr(),
+                                          self.nz_dev.data_ptr(), C.byref(yh), st))
+        self.bounds_host.copy_(self.bounds_dev, non_blocking=True)
+        self.nz_host.copy_(self.nz_dev, non_blocking=True)
+        self._shortcut(use_shortcut)
+        self.g_s.run()
+        torch.cuda.current_stream().synchronize()
+        (hy, wy), (hz, wz) = self.dims_y, self.dims_z
+        sec_z = entropy.encode_z(self.table, self.z_host.numpy().reshape(self.cz, hz, wz))
+        sec_y = entropy.encode_y(self.bounds_host.numpy().view(np.uint32).reshape(self.cy, hy * wy),
+                                 self.nz_host.numpy())
+        if first_of_i_frame:    # bitstream.py:292-296
+            sec_z = (0).to_bytes(4, 'big') * 2 + sec_z
+        return sec_z + sec_y
+
+    def decode(self, sec_z, sec_y, frame_type, use_shortcut):
+        L, st = _lib.lib(), _lib.stream_ptr()
+        _, dec_gain = self.gains[frame_type]
+        (hy, wy), (hz, wz) = self.dims_y, self.dims_z
+        z = entropy.decode_z(self.table, sec_z, self.cz, hz, wz)
+        self.z_host.copy_(torch.from_numpy(z).reshape(-1))
+        self.z_dev.copy_(self.z_host, non_blocking=True)
+        zf = self.h_s.in_fmap
+        _lib.check(L.aivc_i16_to_fmap(self.z_dev.data_ptr(), C.byref(zf), st))
+        self.h_s.run()
+        hsf = self.h_s.out_fmap
+        hs_y = _lib.FMap.from_buffer_copy(hsf)
+        hs_y.h, hs_y.w = hy, wy                       # h_s(z)[:, :, :h_y, :w_y]  decode.py:853
+        _lib.check(L.aivc_laplace_scale(C.byref(hs_y), self.cy, self.b_dev.data_ptr(), st))
+        self.b_host.copy_(self.b_dev, non_blocking=True)
+        self._shortcut(use_shortcut)                  # overlaps the host range decoder
+        torch.cuda.current_stream().synchronize()
+        q = entropy.decode_y(sec_y, self.b_host.numpy().reshape(self.cy, hy, wy), self.cy, hy, wy)
+        self.q_host.copy_(torch.from_numpy(q).reshape(-1))
+        self.q_dev.copy_(self.q_host, non_blocking=True)
+        yh = self._yhat_view()
+        _lib.check(L.aivc_dequantize_latent(self.q_dev.data_ptr(), C.byref(hs_y), dec_gain.data_ptr(),
+                                            C.byref(yh), st))
+        self.g_s.run()
+        self.last = {'z': z, 'q': q}
+
+
+class FrameCodec:
+    """Encoder + decoder of one model at one frame size on one device."""
+
+    def __init__(self, model, h, w, device='cuda:0', cfg=None, idx_rate=0., decoder_only=False):
+        self.h, self.w = h, w
+        self.device = torch.device(device)
+        self.cfg = cfg or Config()
+        self.idx_rate = idx_rate
+        with torch.cuda.device(self.device):
+            self.mof_in = Buffer(h, w, 9, 0, F32, self.device)
+            self.codec_in = Buffer(h, w, 6, 0, F32, self.device)
+            self.skip = Buffer(h, w, 3, 0, F32, self.device)
+            self.mof = CondNetEngine(model.mode_net.mode_net, h, w, self.mof_in, 3, 6, self.device,
+                                     self.cfg, idx_rate)
+            self.codec = CondNetEngine(model.codec_net.codec_net, h, w, self.codec_in, 3, 3,
+                                       self.device, self.cfg, idx_rate)
+            hc, wc = (h + 1) // 2, (w + 1) // 2
+            self.zero_planes = (torch.zeros(h * w, dtype=torch.uint8, device=self.device),
+                                torch.zeros(hc * wc, dtype=torch.uint8, device=self.device),
+                                torch.zeros(hc * wc, dtype=torch.uint8, device=self.device))
+
+    # -- helpers
+    def new_planes(self):
+        hc, wc = (self.h + 1) // 2, (self.w + 1) // 2
+        d = dict(dtype=torch.uint8, device=self.device)
+        return (torch.empty(self.h * self.w, **d), torch.empty(hc * wc, **d), torch.empty(hc * wc, **d))
+
+    def _pack(self, planes, buf, c_off):
+        y, u, v = planes
+        u8 = 1 if y.dtype == torch.uint8 else 0
+        fm = buf.view(c_off, 3)
+        _lib.check(_lib.lib().aivc_yuv420_to_fmap(y.data_ptr(), u.data_ptr(), v.data_ptr(), u8,
+                                                  C.byref(fm), _lib.stream_ptr()))
+
+    def _zero_pred(self):
+        full = self.codec_in.t.view(self.codec_in.rows, self.codec_in.pitch, self.codec_in.c)
+        full[:, :, 3:].zero_()
+
+    def _motion(self, frame_type):
+        L = _lib.lib()
+        mo = self.mof.g_s.out_fmap
+        prev, nxt = self.mof_in.view(3, 3), self.mof_in.view(6, 3)
+        pred, skip = self.codec_in.view(3, 3), self.skip.view(0, 3)
+        _lib.check(L.aivc_warp_blend(C.byref(mo), C.byref(prev), C.byref(nxt),
+                                     1 if frame_type == FRAME_P else 0, C.byref(pred), C.byref(skip),
+                                     _lib.stream_ptr()))
+
+    def _finalize(self, frame_type, out_planes):
+        cod = _lib.FMap.from_buffer_copy(self.codec.g_s.out_fmap)
+        cod.h, cod.w = self.h, self.w                  # crop (decode.py:652)
+        sk = self.skip.view(0, 3)
+        y, u, v = out_planes
+        _lib.check(_lib.lib().aivc_finalize_frame(
+            C.byref(cod), None if frame_type == FRAME_I else C.byref(sk), y.data_ptr(), u.data_ptr(),
+            v.data_ptr(), None, _lib.stream_ptr()))
+
+    def _refs(self, frame_type, prev_rec, next_rec):
+        self._pack(prev_rec if frame_type != FRAME_I else self.zero_planes, self.mof_in, 3)
+        self._pack(next_rec if frame_type == FRAME_B else self.zero_planes, self.mof_in, 6)
+
+    # -- public
+    def encode_frame(self, planes, frame_type, prev_rec=None, next_rec=None):
+        """planes: (y, u, v) flat device tensors, uint8 levels or fp32 in [0,1].
+        Returns (frame bitstream bytes, reconstructed uint8 planes)."""
+        with torch.cuda.device(self.device):
+            data = b''
+            self._pack(planes, self.codec_in, 0)
+            if frame_type == FRAME_I:
+                self._zero_pred()
+            else:
+                self._pack(planes, self.mof_in, 0)
+                self._refs(frame_type, prev_rec, next_rec)
+                data += self.mof.encode(frame_type, frame_type == FRAME_B)
+                self._motion(frame_type)
+            data += self.codec.encode(frame_type, frame_type != FRAME_I,
+                                      first_of_i_frame=(frame_type == FRAME_I))
+            rec = self.new_planes()
+            self._finalize(frame_type, rec)
+        return data, rec
+
+    def decode_frame(self, frame_bytes, frame_type, prev_rec=None, next_rec=None):
+        """Decoder.decode (decode.py:455-580). Returns reconstructed uint8 planes."""
+        with torch.cuda.device(self.device):
+            secs = entropy.split_sections(frame_bytes)
+            if frame_type == FRAME_I:
+                self._zero_pred()
+            else:
+                self._refs(frame_type, prev_rec, next_rec)
+                self.mof.decode(secs[0], secs[1], frame_type, frame_type == FRAME_B)
+                self._motion(frame_type)
+            self.codec.decode(secs[2], secs[3], frame_type, frame_type != FRAME_I)
+            rec = self.new_planes()
+            self._finalize(frame_type, rec)
+        return rec
+
+    def encode_gop(self, frames, gop):
+        """frames: {'frame_i': (y,u,v) device planes}. Returns ({name: bytes}, {name: planes})."""
+        out_b, rec = {}, {}
+        for f in coding_order(gop):
+            e = gop[f]
+            out_b[f], rec[f] = self.encode_frame(frames[f], e['type'], rec.get(e['prev_ref']),
+                                                 rec.get(e['next_ref']))
+        return out_b, rec
+
+    def decode_gop(self, frame_bytes, gop):
+        rec = {}
+        for f in coding_order(gop):
+            e = gop[f]
+            rec[f] = self.decode_frame(frame_bytes[f], e['type'], rec.get(e['prev_ref']),
+                                       rec.get(e['next_ref']))
+        return rec
+
+
+def planes_to_device(yuv_u8, device):
+    """(y, u, v) numpy uint8 arrays -> flat device tensors."""
+    return tuple(torch.from_numpy(np.ascontiguousarray(p).reshape(-1)).to(device) for p in yuv_u8)
+
+
+def gop_forward(model, model_input):
+    raise NotImplementedError('FullNet.GOP_forward adapter: see aivc_b200.adapter')

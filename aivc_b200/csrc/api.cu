@@ -1,0 +1,79 @@
+// C-ABI glue: error reporting, argument validation, engine dispatch.
+#include <stdarg.h>
+#include "common.cuh"
+#include "laplace_cdf.h"
+
+int conv_simt_run(const aivc_conv_op *op, cudaStream_t st);
+int conv_tc_run(const aivc_conv_op *op, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void aivc_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int validate_fmap(const aivc_fmap *m, const char *what) {
+    if (!m || !m->data) AIVC_FAIL("%s: null feature map", what);
+    if (m->h <= 0 || m->w <= 0 || m->c <= 0) AIVC_FAIL("%s: empty feature map %dx%dx%d", what, m->h, m->w, m->c);
+    if (m->c_off < 0 || m->c_off + m->c > m->c_stride) AIVC_FAIL("%s: channel view [%d,%d) exceeds pixel stride %d", what, m->c_off, m->c_off + m->c, m->c_stride);
+    if (m->pad < 0 || m->pitch < m->w + 2 * m->pad || m->rows < m->h + 2 * m->pad) AIVC_FAIL("%s: pitch/rows smaller than padded size", what);
+    if (m->dtype != AIVC_F32 && m->dtype != AIVC_BF16) AIVC_FAIL("%s: unknown dtype %d", what, m->dtype);
+    return 0;
+}
+
+static int validate_conv(const aivc_conv_op *op) {
+    if (!op) AIVC_FAIL("conv2d_fused: null op");
+    if (validate_fmap(&op->in, "conv in") || validate_fmap(&op->out, "conv out")) return 1;
+    if (!op->weight) AIVC_FAIL("conv2d_fused: null weight");
+    if (op->k < 1 || (op->k & 1) == 0) AIVC_FAIL("conv2d_fused: kernel size %d must be odd", op->k);
+    if (op->kind == 0) {
+        if (op->stride != 1 && op->stride != 2) AIVC_FAIL("conv2d_fused: stride %d unsupported", op->stride);
+        const int eh = (op->in.h + op->stride - 1) / op->stride, ew = (op->in.w + op->stride - 1) / op->stride;
+        if (op->out.h != eh || op->out.w != ew) AIVC_FAIL("conv2d_fused: output %dx%d, expected %dx%d", op->out.h, op->out.w, eh, ew);
+    } else if (op->kind == 1) {
+        if (op->stride != 2) AIVC_FAIL("conv2d_fused: transposed conv needs stride 2");
+        if (op->out.h != 2 * op->in.h || op->out.w != 2 * op->in.w) AIVC_FAIL("conv2d_fused: transposed output must be exactly 2x");
+    } else {
+        AIVC_FAIL("conv2d_fused: unknown kind %d", op->kind);
+    }
+    if ((op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN) && (!op->gdn_beta || !op->gdn_gamma)) AIVC_FAIL("conv2d_fused: GDN without parameters");
+    if (op->residual.data) {
+        if (validate_fmap(&op->residual, "conv residual")) return 1;
+        if (op->residual.h != op->out.h || op->residual.w != op->out.w || op->residual.c != op->out.c) AIVC_FAIL("conv2d_fused: residual shape mismatch");
+    }
+    if (op->gate.data) {
+        if (validate_fmap(&op->gate, "conv gate")) return 1;
+        if (op->gate.h != op->out.h || op->gate.w != op->out.w || op->gate.c != op->out.c) AIVC_FAIL("conv2d_fused: gate shape mismatch");
+    }
+    return 0;
+}
+
+extern "C" {
+
+int aivc_abi_version(void) { return AIVC_ABI_VERSION; }
+const char *aivc_last_error(void) { return g_err; }
+
+int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
+    if (validate_conv(op)) return 1;
+    if (op->engine == AIVC_ENGINE_SIMT) return conv_simt_run(op, (cudaStream_t)stream);
+    if (op->engine == AIVC_ENGINE_TC) return conv_tc_run(op, (cudaStream_t)stream);
+    AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
+}
+
+int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
+    for (int i = 0; i < n; ++i)
+        if (aivc_conv2d_fused(ops + i, stream)) {
+            char tmp[400];
+            snprintf(tmp, sizeof(tmp), "%s", g_err);
+            AIVC_FAIL("stage %d/%d: %s", i, n, tmp);
+        }
+    return 0;
+}
+
+uint32_t aivc_laplace_cdf_int_host(float b, int i) { return aivc_laplace_cdf_int(b, i); }
+float aivc_sigma_from_logvar_host(float v) { return aivc_sigma_from_logvar(v); }
+
+}  // extern "C"

@@ -42,9 +42,9 @@
 #define AIVC_CDF_SCALE 65023.0f   /* 2^16 - (Lp - 1) */
 #define AIVC_SQRT2_F 1.41421354f  /* fp32 sqrt(2), as torch.sqrt(torch.tensor([2.0])) */
 
-// expm1(x) for x <= 0, |error| ~1e-16: k = rint(x*log2e), r = x - k*ln2, Taylor(12) for e^r - 1.
-AIVC_HD double aivc_expm1_neg(double x) {
-    if (x <= -20.0) return -1.0;     // e^x < 2^-28: the fp32 result is exactly -1
+// e^x = 2^k (1 + p): k = rint(x*log2e), r = x - k*ln2 (two-part ln2), p = Taylor(12)(r) - 1.
+// |error| ~1e-16; only IEEE add/mul/fma, so host and device agree bit for bit.
+AIVC_HD double aivc_exp_parts(double x, double *two_k_out) {
     const double k = rint(AIVC_MUL(x, 1.4426950408889634));
     double r = AIVC_FMA(-k, 6.93147180369123816490e-01, x);
     r = AIVC_FMA(-k, 1.90821492927058770002e-10, r);
@@ -59,10 +59,26 @@ AIVC_HD double aivc_expm1_neg(double x) {
     e = AIVC_FMA(e, r, 4.16666666666666666667e-02);         // 1/4!
     e = AIVC_FMA(e, r, 1.66666666666666666667e-01);         // 1/3!
     e = AIVC_FMA(e, r, 0.5);                                // 1/2!
-    const double p = AIVC_FMA(AIVC_MUL(e, r), r, r);        // e^r - 1
     union { uint64_t u; double d; } two_k;
-    two_k.u = (uint64_t)(1023 + (int)k) << 52;              // 2^k, k in [-29, 0]
-    return AIVC_FMA(two_k.d, p, AIVC_SUB(two_k.d, 1.0));
+    two_k.u = (uint64_t)(1023 + (int)k) << 52;              // 2^k, |k| small
+    *two_k_out = two_k.d;
+    return AIVC_FMA(AIVC_MUL(e, r), r, r);                  // e^r - 1
+}
+
+// expm1(x) for x <= 0
+AIVC_HD double aivc_expm1_neg(double x) {
+    if (x <= -20.0) return -1.0;     // e^x < 2^-28: the fp32 result is exactly -1
+    double two_k;
+    const double p = aivc_exp_parts(x, &two_k);
+    return AIVC_FMA(two_k, p, AIVC_SUB(two_k, 1.0));
+}
+
+// sigma = exp(0.5 * clamp(v, LOG_VAR_MIN, LOG_VAR_MAX))   misc_layers.py:214-221
+AIVC_HD float aivc_sigma_from_logvar(float v) {
+    const float c = fminf(fmaxf(v, -18.4207f), 10.0f);
+    double two_k;
+    const double p = aivc_exp_parts((double)AIVC_FMULF(0.5f, c), &two_k);
+    return (float)AIVC_FMA(two_k, p, two_k);
 }
 
 // b = sigma / sqrt(2) in fp32 (bitstream.py:141)

@@ -1,0 +1,493 @@
+// HBM-bound kernels of the hot path: layout bridges, pixel ends (4:2:0 <-> 4:4:4, 8-bit cast),
+// motion-compensation warp + blend, hyperprior mu/sigma, quantisation + integer CDF bounds.
+// One thread per pixel (or per symbol); channel counts here are 1..6 at full resolution and
+// C_y at latent resolution, so the work is a single pass over the data.
+#include "common.cuh"
+#include "laplace_cdf.h"
+
+namespace {
+
+constexpr int PT = 256;
+
+// ---------------------------------------------------------------- layout bridges
+__global__ void nchw_to_fmap_kernel(const float *__restrict__ src, FMap dst) {
+    const int hw = dst.h * dst.w;
+    const size_t n = (size_t)hw * dst.c;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % dst.c);
+        const int pix = (int)(i / dst.c);
+        fm_store(dst, pix / dst.w, pix % dst.w, ch, src[(size_t)ch * hw + pix]);
+    }
+}
+
+__global__ void fmap_to_nchw_kernel(FMap src, float *__restrict__ dst) {
+    const int hw = src.h * src.w;
+    const size_t n = (size_t)hw * src.c;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % hw);
+        const int ch = (int)(i / hw);
+        dst[i] = fm_load(src, pix / src.w, pix % src.w, ch);
+    }
+}
+
+__global__ void fill_border_kernel(FMap m) {
+    // one thread per padded pixel of the border ring
+    const int hp = m.h + 2 * m.pad, wp = m.w + 2 * m.pad;
+    const size_t n = (size_t)hp * wp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int yp = (int)(i / wp), xp = (int)(i % wp);
+        const int y = min(max(yp - m.pad, 0), m.h - 1), x = min(max(xp - m.pad, 0), m.w - 1);
+        if (y + m.pad == yp && x + m.pad == xp) continue;
+        for (int ch = 0; ch < m.c; ++ch) fm_store_raw(m, yp, xp, ch, fm_load(m, y, x, ch));
+    }
+}
+
+__global__ void fmap_to_i16_kernel(FMap src, int16_t *__restrict__ dst) {
+    const int hw = src.h * src.w;
+    const size_t n = (size_t)hw * src.c;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % hw), ch = (int)(i / hw);
+        dst[i] = (int16_t)fm_load(src, pix / src.w, pix % src.w, ch);
+    }
+}
+
+__global__ void i16_to_fmap_kernel(const int16_t *__restrict__ src, FMap dst) {
+    const int hw = dst.h * dst.w;
+    const size_t n = (size_t)hw * dst.c;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % dst.c), pix = (int)(i / dst.c);
+        fm_store(dst, pix / dst.w, pix % dst.w, ch, (float)src[(size_t)ch * hw + pix]);
+    }
+}
+
+// ---------------------------------------------------------------- InputLayer
+template <bool U8>
+__global__ void yuv420_to_fmap_kernel(const void *__restrict__ yp, const void *__restrict__ up,
+                                      const void *__restrict__ vp, FMap dst) {
+    const int wc = (dst.w + 1) / 2;
+    const size_t n = (size_t)dst.h * dst.w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / dst.w), x = (int)(i % dst.w);
+        const size_t ci = (size_t)(y / 2) * wc + (x / 2);
+        float a, b, c;
+        if (U8) {
+            a = (float)((const uint8_t *)yp)[i] / 255.f;
+            b = (float)((const uint8_t *)up)[ci] / 255.f;
+            c = (float)((const uint8_t *)vp)[ci] / 255.f;
+        } else {
+            a = ((const float *)yp)[i];
+            b = ((const float *)up)[ci];
+            c = ((const float *)vp)[ci];
+        }
+        fm_store(dst, y, x, 0, a);
+        fm_store(dst, y, x, 1, b);
+        fm_store(dst, y, x, 2, c);
+    }
+}
+
+// ---------------------------------------------------------------- warp
+// grid_sample(bilinear, border, align_corners=True) at (x + fx, y + fy), following the fp32
+// operation order of func_util/optical_flow.py:28-41 + ATen's grid sampler.
+struct Bilerp {
+    int x0, y0, x1, y1;
+    float w00, w01, w10, w11;   // nw, ne, sw, se
+};
+
+__device__ __forceinline__ Bilerp bilerp_setup(int x, int y, float fx, float fy, int w, int h) {
+    const float wm = (float)max(w - 1, 1), hm = (float)max(h - 1, 1);
+    float gx = 2.0f * ((float)x + fx) / wm - 1.0f;       // normalise (optical_flow.py:31-32)
+    float gy = 2.0f * ((float)y + fy) / hm - 1.0f;
+    float ix = ((gx + 1.f) / 2.f) * (float)(w - 1);      // un-normalise (align_corners=True)
+    float iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));          // border padding = clip coordinates
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+    const float xf = floorf(ix), yf = floorf(iy);
+    Bilerp b;
+    b.x0 = (int)xf; b.y0 = (int)yf;
+    b.x1 = b.x0 + 1; b.y1 = b.y0 + 1;
+    const float ex = (xf + 1.f) - ix, ey = (yf + 1.f) - iy;   // distance to the se corner
+    const float dx = ix - xf, dy = iy - yf;
+    b.w00 = ex * ey; b.w01 = dx * ey; b.w10 = ex * dy; b.w11 = dx * dy;
+    return b;
+}
+
+template <typename L>
+__device__ __forceinline__ float bilerp_sample(const Bilerp &b, int w, int h, L load) {
+    // out-of-range corners (x1 == w or y1 == h) carry zero weight; skip their loads
+    float acc = 0.f;
+    acc += load(b.y0, b.x0) * b.w00;
+    if (b.x1 < w) acc += load(b.y0, b.x1) * b.w01;
+    if (b.y1 < h) acc += load(b.y1, b.x0) * b.w10;
+    if (b.x1 < w && b.y1 < h) acc += load(b.y1, b.x1) * b.w11;
+    return acc;
+}
+
+__global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p, FMap pred,
+                                  FMap skip) {
+    const int h = pred.h, w = pred.w;
+    const size_t n = (size_t)h * w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i % w);
+        const float alpha = fminf(fmaxf(fm_load(mof, y, x, 0) + 0.5f, 0.f), 1.f);
+        float beta = fminf(fmaxf(fm_load(mof, y, x, 1) + 0.5f, 0.f), 1.f);
+        const Bilerp bp = bilerp_setup(x, y, fm_load(mof, y, x, 2), fm_load(mof, y, x, 3), w, h);
+        Bilerp bn;
+        if (frame_is_p) {
+            beta = 1.f;
+            bn = bilerp_setup(x, y, 0.f, 0.f, w, h);
+        } else {
+            bn = bilerp_setup(x, y, fm_load(mof, y, x, 4), fm_load(mof, y, x, 5), w, h);
+        }
+        for (int ch = 0; ch < 3; ++ch) {
+            const float a = bilerp_sample(bp, w, h, [&](int yy, int xx) { return fm_load(prev, yy, xx, ch); });
+            const float b = bilerp_sample(bn, w, h, [&](int yy, int xx) { return fm_load(next, yy, xx, ch); });
+            const float xw = beta * a + (1.f - beta) * b;
+            fm_store(pred, y, x, ch, xw * alpha);             // warped_ref * alpha  (decode.py:542)
+            fm_store(skip, y, x, ch, (1.f - alpha) * xw);     // (1 - alpha) * warped (decode.py:536)
+        }
+    }
+}
+
+__global__ void warp_blend_nchw_kernel(const float *__restrict__ prev, const float *__restrict__ next,
+                                       const float *__restrict__ vp, const float *__restrict__ vn,
+                                       const float *__restrict__ beta, float *__restrict__ out, int h,
+                                       int w) {
+    const size_t n = (size_t)h * w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i % w);
+        const Bilerp bp = bilerp_setup(x, y, vp[i], vp[n + i], w, h);
+        const Bilerp bn = bilerp_setup(x, y, vn[i], vn[n + i], w, h);
+        for (int ch = 0; ch < 3; ++ch) {
+            const float *pc = prev + ch * n, *nc = next + ch * n;
+            const float a = bilerp_sample(bp, w, h, [&](int yy, int xx) { return pc[(size_t)yy * w + xx]; });
+            const float b = bilerp_sample(bn, w, h, [&](int yy, int xx) { return nc[(size_t)yy * w + xx]; });
+            const float be = beta[ch * n + i];
+            out[ch * n + i] = be * a + (1.f - be) * b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- OutputLayer + 8-bit cast
+__device__ __forceinline__ float level8(float v) {
+    return rintf(255.f * fminf(fmaxf(v, 0.f), 1.f));
+}
+
+__global__ void finalize_frame_kernel(FMap codec, FMap skip, uint8_t *__restrict__ yo,
+                                      uint8_t *__restrict__ uo, uint8_t *__restrict__ vo, FMap ref,
+                                      int h, int w) {
+    // one thread per chroma sample = 2x2 luma block
+    const int hc = (h + 1) / 2, wc = (w + 1) / 2;
+    const int hc_valid = h / 2, wc_valid = w / 2;      // bilinear x0.5 yields floor(h/2) rows
+    const size_t n = (size_t)hc * wc;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int cy = (int)(i / wc), cx = (int)(i % wc);
+        auto val = [&](int yy, int xx, int ch) {
+            float v = fm_load(codec, yy, xx, ch);
+            if (skip.data) v += fm_load(skip, yy, xx, ch);
+            return v;
+        };
+        // luma
+        float ylev[2][2];
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                const int yy = 2 * cy + dy, xx = 2 * cx + dx;
+                if (yy < h && xx < w) {
+                    ylev[dy][dx] = level8(val(yy, xx, 0));
+                    yo[(size_t)yy * w + xx] = (uint8_t)ylev[dy][dx];
+                }
+            }
+        // chroma: mean of the 2x2 block; the last row/col of an odd-sized frame replicates
+        // its neighbour (decode.py:562-571)
+        const int sy = min(cy, max(hc_valid - 1, 0)), sx = min(cx, max(wc_valid - 1, 0));
+        float lev[2];
+        for (int ch = 1; ch < 3; ++ch) {
+            float m;
+            if (hc_valid == 0 || wc_valid == 0) {
+                m = val(min(2 * sy, h - 1), min(2 * sx, w - 1), ch);
+            } else {
+                const float a = val(2 * sy, 2 * sx, ch), b = val(2 * sy, 2 * sx + 1, ch);
+                const float c = val(2 * sy + 1, 2 * sx, ch), d = val(2 * sy + 1, 2 * sx + 1, ch);
+                m = 0.5f * (0.5f * a + 0.5f * b) + 0.5f * (0.5f * c + 0.5f * d);
+            }
+            lev[ch - 1] = level8(m);
+        }
+        uo[i] = (uint8_t)lev[0];
+        vo[i] = (uint8_t)lev[1];
+        if (ref.data) {
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int yy = 2 * cy + dy, xx = 2 * cx + dx;
+                    if (yy < h && xx < w) {
+                        fm_store(ref, yy, xx, 0, ylev[dy][dx] / 255.f);
+                        fm_store(ref, yy, xx, 1, lev[0] / 255.f);
+                        fm_store(ref, yy, xx, 2, lev[1] / 255.f);
+                    }
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- hyperprior / quantisation
+__global__ void mu_sigma_nchw_kernel(const float *__restrict__ hs, float *__restrict__ mu,
+                                     float *__restrict__ sigma, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        mu[i] = hs[i];
+        sigma[i] = aivc_sigma_from_logvar(hs[n + i]);
+    }
+}
+
+__global__ void quantize_latent_kernel(FMap y, FMap hs, const float *__restrict__ dec_gain,
+                                       int16_t *__restrict__ q, uint32_t *__restrict__ bounds,
+                                       int32_t *__restrict__ nz, FMap yhat) {
+    const int c = y.c, hw = y.h * y.w;
+    const size_t n = (size_t)c * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c), pix = (int)(i / c);
+        const int yy = pix / y.w, xx = pix % y.w;
+        const float mu = fm_load(hs, yy, xx, ch);
+        const float sigma = aivc_sigma_from_logvar(fm_load(hs, yy, xx, c + ch));
+        const float v = fm_load(y, yy, xx, ch);
+        const float qf = fminf(fmaxf(rintf(v - mu), -256.f), 255.f);
+        const int qi = (int)qf;
+        const float b = aivc_laplace_scale(sigma);
+        const uint32_t lo = aivc_laplace_cdf_int(b, qi + 256), hi = aivc_laplace_cdf_int(b, qi + 257);
+        const size_t o = (size_t)ch * hw + pix;
+        q[o] = (int16_t)qi;
+        bounds[o] = lo | (hi << 16);
+        if (qi != 0) nz[ch] = 1;
+        if (yhat.data) fm_store(yhat, yy, xx, ch, (qf + mu) * dec_gain[ch]);
+    }
+}
+
+__global__ void laplace_scale_kernel(FMap hs, int c, float *__restrict__ b) {
+    const int hw = hs.h * hs.w;
+    const size_t n = (size_t)c * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c), pix = (int)(i / c);
+        const float sigma = aivc_sigma_from_logvar(fm_load(hs, pix / hs.w, pix % hs.w, c + ch));
+        b[(size_t)ch * hw + pix] = aivc_laplace_scale(sigma);
+    }
+}
+
+__global__ void dequantize_latent_kernel(const int16_t *__restrict__ q, FMap hs,
+                                         const float *__restrict__ dec_gain, FMap yhat) {
+    const int c = yhat.c, hw = yhat.h * yhat.w;
+    const size_t n = (size_t)c * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c), pix = (int)(i / c);
+        const int yy = pix / yhat.w, xx = pix % yhat.w;
+        const float mu = fm_load(hs, yy, xx, ch);
+        fm_store(yhat, yy, xx, ch, ((float)q[(size_t)ch * hw + pix] + mu) * dec_gain[ch]);
+    }
+}
+
+// ---------------------------------------------------------------- weight re-layout
+__global__ void pack_weight_kernel(const float *__restrict__ src, void *__restrict__ dst, int kind,
+                                   int k, int cin, int cout, int engine, int cin_pad, int cout_pad) {
+    const int taps = k * k;
+    const size_t n = (engine == AIVC_ENGINE_SIMT) ? (size_t)taps * cin * cout
+                                                  : (size_t)taps * cout_pad * cin_pad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        int t, ci, co;
+        if (engine == AIVC_ENGINE_SIMT) {          // [tap][cin][cout]
+            co = (int)(i % cout); ci = (int)((i / cout) % cin); t = (int)(i / ((size_t)cout * cin));
+        } else {                                   // [tap][cout_pad][cin_pad]
+            ci = (int)(i % cin_pad); co = (int)((i / cin_pad) % cout_pad);
+            t = (int)(i / ((size_t)cin_pad * cout_pad));
+        }
+        float v = 0.f;
+        if (ci < cin && co < cout) {
+            // Conv2d weight [cout][cin][k][k]; ConvTranspose2d weight [cin][cout][k][k]
+            const size_t s = (kind == 0) ? (((size_t)co * cin + ci) * taps + t)
+                                         : (((size_t)ci * cout + co) * taps + t);
+            v = src[s];
+        }
+        if (engine == AIVC_ENGINE_SIMT) ((float *)dst)[i] = v;
+        else ((__nv_bfloat16 *)dst)[i] = __float2bfloat16_rn(v);
+    }
+}
+
+int grid_for(size_t n) {
+    size_t g = (n + PT - 1) / PT;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int aivc_nchw_to_fmap(const float *src, const aivc_fmap *dst, void *stream) {
+    if (validate_fmap(dst, "nchw_to_fmap dst")) return 1;
+    nchw_to_fmap_kernel<<<grid_for((size_t)dst->h * dst->w * dst->c), PT, 0, (cudaStream_t)stream>>>(
+        src, to_dev(*dst));
+    AIVC_CHECK_LAUNCH("nchw_to_fmap");
+    return 0;
+}
+
+int aivc_fmap_to_nchw(const aivc_fmap *src, float *dst, void *stream) {
+    if (validate_fmap(src, "fmap_to_nchw src")) return 1;
+    fmap_to_nchw_kernel<<<grid_for((size_t)src->h * src->w * src->c), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*src), dst);
+    AIVC_CHECK_LAUNCH("fmap_to_nchw");
+    return 0;
+}
+
+int aivc_fill_border(const aivc_fmap *m, void *stream) {
+    if (validate_fmap(m, "fill_border")) return 1;
+    if (m->pad == 0) return 0;
+    fill_border_kernel<<<grid_for((size_t)(m->h + 2 * m->pad) * (m->w + 2 * m->pad)), PT, 0,
+                         (cudaStream_t)stream>>>(to_dev(*m));
+    AIVC_CHECK_LAUNCH("fill_border");
+    return 0;
+}
+
+int aivc_fmap_to_i16(const aivc_fmap *src, int16_t *dst, void *stream) {
+    if (validate_fmap(src, "fmap_to_i16 src")) return 1;
+    fmap_to_i16_kernel<<<grid_for((size_t)src->h * src->w * src->c), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*src), dst);
+    AIVC_CHECK_LAUNCH("fmap_to_i16");
+    return 0;
+}
+
+int aivc_i16_to_fmap(const int16_t *src, const aivc_fmap *dst, void *stream) {
+    if (validate_fmap(dst, "i16_to_fmap dst")) return 1;
+    i16_to_fmap_kernel<<<grid_for((size_t)dst->h * dst->w * dst->c), PT, 0, (cudaStream_t)stream>>>(
+        src, to_dev(*dst));
+    AIVC_CHECK_LAUNCH("i16_to_fmap");
+    return 0;
+}
+
+int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, const aivc_fmap *dst,
+                        void *stream) {
+    if (validate_fmap(dst, "yuv420_to_fmap dst")) return 1;
+    if (dst->c != 3) AIVC_FAIL("yuv420_to_fmap: destination view must have 3 channels, got %d", dst->c);
+    const int g = grid_for((size_t)dst->h * dst->w);
+    if (u8) yuv420_to_fmap_kernel<true><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst));
+    else yuv420_to_fmap_kernel<false><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst));
+    AIVC_CHECK_LAUNCH("yuv420_to_fmap");
+    return 0;
+}
+
+int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
+                    int frame_is_p, const aivc_fmap *pred, const aivc_fmap *skip, void *stream) {
+    if (validate_fmap(mof, "warp mof") || validate_fmap(prev, "warp prev") ||
+        validate_fmap(next, "warp next") || validate_fmap(pred, "warp pred") ||
+        validate_fmap(skip, "warp skip"))
+        return 1;
+    if (mof->c < 6 || mof->h < pred->h || mof->w < pred->w)
+        AIVC_FAIL("warp_blend: MOFNet output must be >= 6 ch and cover the frame");
+    if (prev->h != pred->h || prev->w != pred->w || next->h != pred->h || next->w != pred->w)
+        AIVC_FAIL("warp_blend: reference / prediction size mismatch");
+    warp_blend_kernel<<<grid_for((size_t)pred->h * pred->w), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*mof), to_dev(*prev), to_dev(*next), frame_is_p, to_dev(*pred), to_dev(*skip));
+    AIVC_CHECK_LAUNCH("warp_blend");
+    return 0;
+}
+
+int aivc_warp_blend_nchw(const float *prev, const float *next, const float *v_prev,
+                         const float *v_next, const float *beta, float *out, int h, int w,
+                         void *stream) {
+    warp_blend_nchw_kernel<<<grid_for((size_t)h * w), PT, 0, (cudaStream_t)stream>>>(
+        prev, next, v_prev, v_next, beta, out, h, w);
+    AIVC_CHECK_LAUNCH("warp_blend_nchw");
+    return 0;
+}
+
+int aivc_finalize_frame(const aivc_fmap *codec, const aivc_fmap *skip, uint8_t *y, uint8_t *u,
+                        uint8_t *v, const aivc_fmap *ref444, void *stream) {
+    if (validate_fmap(codec, "finalize codec")) return 1;
+    FMap sk, rf;
+    memset(&sk, 0, sizeof(sk));
+    memset(&rf, 0, sizeof(rf));
+    int h = codec->h, w = codec->w;
+    if (skip && skip->data) {
+        if (validate_fmap(skip, "finalize skip")) return 1;
+        sk = to_dev(*skip);
+        h = skip->h; w = skip->w;
+    }
+    if (ref444 && ref444->data) {
+        if (validate_fmap(ref444, "finalize ref444")) return 1;
+        rf = to_dev(*ref444);
+        h = ref444->h; w = ref444->w;
+    }
+    if (codec->h < h || codec->w < w || codec->c < 3) AIVC_FAIL("finalize: codec output too small");
+    finalize_frame_kernel<<<grid_for((size_t)((h + 1) / 2) * ((w + 1) / 2)), PT, 0,
+                            (cudaStream_t)stream>>>(to_dev(*codec), sk, y, u, v, rf, h, w);
+    AIVC_CHECK_LAUNCH("finalize_frame");
+    return 0;
+}
+
+int aivc_mu_sigma_nchw(const float *hs, float *mu, float *sigma, int c, int hw, void *stream) {
+    const size_t n = (size_t)c * hw;
+    mu_sigma_nchw_kernel<<<grid_for(n), PT, 0, (cudaStream_t)stream>>>(hs, mu, sigma, n);
+    AIVC_CHECK_LAUNCH("mu_sigma_nchw");
+    return 0;
+}
+
+int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *dec_gain, int16_t *q,
+                         uint32_t *bounds, int32_t *nz, const aivc_fmap *yhat, void *stream) {
+    if (validate_fmap(y, "quantize y") || validate_fmap(hs, "quantize hs")) return 1;
+    if (hs->c < 2 * y->c || hs->h < y->h || hs->w < y->w)
+        AIVC_FAIL("quantize_latent: hyper-decoder output must be >= 2C channels and cover y");
+    FMap yh;
+    memset(&yh, 0, sizeof(yh));
+    if (yhat && yhat->data) {
+        if (validate_fmap(yhat, "quantize yhat")) return 1;
+        yh = to_dev(*yhat);
+    }
+    quantize_latent_kernel<<<grid_for((size_t)y->c * y->h * y->w), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*y), to_dev(*hs), dec_gain, q, bounds, nz, yh);
+    AIVC_CHECK_LAUNCH("quantize_latent");
+    return 0;
+}
+
+int aivc_laplace_scale(const aivc_fmap *hs, int c, float *b, void *stream) {
+    if (validate_fmap(hs, "laplace_scale hs")) return 1;
+    if (hs->c < 2 * c) AIVC_FAIL("laplace_scale: need 2C channels");
+    laplace_scale_kernel<<<grid_for((size_t)c * hs->h * hs->w), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*hs), c, b);
+    AIVC_CHECK_LAUNCH("laplace_scale");
+    return 0;
+}
+
+int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *dec_gain,
+                           const aivc_fmap *yhat, void *stream) {
+    if (validate_fmap(hs, "dequantize hs") || validate_fmap(yhat, "dequantize yhat")) return 1;
+    dequantize_latent_kernel<<<grid_for((size_t)yhat->c * yhat->h * yhat->w), PT, 0,
+                               (cudaStream_t)stream>>>(q, to_dev(*hs), dec_gain, to_dev(*yhat));
+    AIVC_CHECK_LAUNCH("dequantize_latent");
+    return 0;
+}
+
+size_t aivc_packed_weight_bytes(int k, int cin, int cout, int engine, int cin_pad, int cout_pad) {
+    if (engine == AIVC_ENGINE_SIMT) return (size_t)k * k * cin * cout * sizeof(float);
+    return (size_t)k * k * cin_pad * cout_pad * 2;
+}
+
+int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin, int cout, int engine,
+                          int cin_pad, int cout_pad, void *stream) {
+    if (engine != AIVC_ENGINE_SIMT && (cin_pad < cin || cout_pad < cout))
+        AIVC_FAIL("pack_conv_weight: padded sizes smaller than logical sizes");
+    const size_t n = aivc_packed_weight_bytes(k, cin, cout, engine, cin_pad, cout_pad) /
+                     (engine == AIVC_ENGINE_SIMT ? 4 : 2);
+    pack_weight_kernel<<<grid_for(n), PT, 0, (cudaStream_t)stream>>>(src, dst, kind, k, cin, cout,
+                                                                     engine, cin_pad, cout_pad);
+    AIVC_CHECK_LAUNCH("pack_weight");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,395 @@
+"""Lowering of AIVC layer trees to fused convolution stages, and their execution.
+
+A transform (``g_a``, ``g_s``, ``h_a``, ``h_s``, ``g_a_ref`` or any single layer) is a tree of
+``Sequential`` / ``CustomConvLayer`` / ``UpscalingLayer`` / ``ChengResBlock`` / ``ResBlock`` /
+``AttentionResBlock`` / ``SimplifiedAttention`` / ``Conv2d`` ... nodes.  ``lower`` walks it by
+class *name* (so reference modules, un-pickled models and the mirrors in
+``aivc_b200.layers`` are all accepted) and emits one ``aivc_conv_op`` per convolution with
+everything that follows it folded into the epilogue:
+
+    out = post( act(conv(in) + bias) * gate + residual ) * out_scale
+
+  ChengResBlock plain/down/up  -> residual of the 2nd conv   (custom_conv_layers.py:105-109)
+  ResBlock / AttentionResBlock -> residual + post ReLU/Leaky  (custom_conv_layers.py:126, attention.py:41)
+  SimplifiedAttention          -> sigmoid act, gate = trunk, residual = x   (attention.py:90-97)
+  GDN / IGDN                   -> act of the producing conv   (misc_layers.py:113-154)
+
+Activations live in NHWC buffers with a replicate border (see include/aivc_b200.h); buffers are
+recycled by liveness.  All stages of a plan run with ONE ctypes call
+(``aivc_conv2d_fused_seq``) on the current CUDA stream.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import FMap, ConvOp, ACT, POST, F32, BF16, ENGINE_SIMT, ENGINE_TC
+
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+@dataclass
+class Config:
+    precision: str = 'bf16'        # 'fp32': every stage on the exact SIMT engine, fp32 buffers
+                                   # 'bf16': tcgen05 engine wherever the channel counts allow
+    tc_min_cin: int = 16           # tensor-core stages need cin % 16 == 0 and cout % 16 == 0
+
+    def key(self):
+        return (self.precision, self.tc_min_cin)
+
+
+DEFAULT = Config()
+
+
+class Buffer:
+    """One device allocation holding a bordered NHWC tensor."""
+
+    def __init__(self, h, w, c, pad, dtype, device):
+        self.h, self.w, self.c, self.pad, self.dtype = h, w, c, pad, dtype
+        self.pitch = w + 2 * pad + ((w + 2 * pad) & 1)      # even: stride-2 TMA views pair columns
+        self.rows = h + 2 * pad + ((h + 2 * pad) & 1)
+        self.t = torch.zeros(self.rows * self.pitch * c, dtype=_TORCH_DT[dtype], device=device)
+
+    def view(self, c_off=0, c=None, h=None, w=None):
+        return FMap(self.t.data_ptr(), self.h if h is None else h, self.w if w is None else w,
+                    self.c - c_off if c is None else c, c_off, self.c, self.pad, self.pitch,
+                    self.rows, self.dtype, 0)
+
+    def interior(self):
+        """[h, w, c] torch view of the logical tensor (debug / tests)."""
+        full = self.t.view(self.rows, self.pitch, self.c)
+        return full[self.pad:self.pad + self.h, self.pad:self.pad + self.w]
+
+
+@dataclass
+class T:
+    """Symbolic tensor of a plan."""
+    h: int
+    w: int
+    c: int
+    pad: int = 0
+    dtype: int = F32
+    buf: Optional[Buffer] = None
+    c_off: int = 0
+    external: bool = False
+    first: int = 10 ** 9
+    last: int = -1
+
+    def fmap(self):
+        return self.buf.view(self.c_off, self.c, self.h, self.w)
+
+
+@dataclass
+class Stage:
+    kind: int
+    k: int
+    stride: int
+    src: T
+    dst: T
+    weight: torch.Tensor            # original layout, fp32
+    bias: Optional[torch.Tensor]
+    act: str = 'no'
+    post: str = 'none'
+    gdn: Optional[tuple] = None     # (beta, gamma, inverse)
+    res: Optional[T] = None
+    gate: Optional[T] = None
+    out_scale: Optional[torch.Tensor] = None
+    engine: int = ENGINE_SIMT
+    keep: list = field(default_factory=list)   # device tensors referenced by the op
+
+
+class Graph:
+    def __init__(self):
+        self.stages = []
+
+    def conv(self, kind, k, stride, src, weight, bias, act='no', gdn=None):
+        if kind == 0:
+            cout = weight.shape[0]
+            h, w = -(-src.h // stride), -(-src.w // stride)
+        else:
+            cout = weight.shape[1]
+            h, w = 2 * src.h, 2 * src.w
+        dst = T(h, w, cout)
+        self.stages.append(Stage(kind, k, stride, src, dst, weight.detach(), None if bias is None
+                                 else bias.detach(), act, gdn=gdn))
+        return dst
+
+
+def _act_of(m):
+    n = type(m).__name__
+    if n == 'LeakyReLU':
+        if abs(m.negative_slope - 0.01) > 1e-12:
+            raise NotImplementedError('LeakyReLU slope != 0.01')
+        return 'leaky_relu'
+    return {'ReLU': 'relu', 'Sigmoid': 'sigmoid'}.get(n)
+
+
+def _gdn_params(m):
+    dev = m.beta.device
+    ped = m.pedestal.to(dev)
+    beta = torch.maximum(m.beta.detach(), m.beta_bound.to(dev)) ** 2 - ped
+    gamma = torch.maximum(m.gamma.detach(), m.gamma_bound.to(dev)) ** 2 - ped
+    return beta.float(), gamma.float(), bool(m.inverse)
+
+
+def _lower_seq(seq, x, g):
+    children = list(seq)
+    i = 0
+    while i < len(children):
+        m = children[i]
+        n = type(m).__name__
+        if n == 'ReplicationPad2d':
+            nxt = children[i + 1]
+            if type(nxt).__name__ != 'Conv2d' or m.padding[0] != nxt.kernel_size[0] // 2:
+                raise NotImplementedError('ReplicationPad2d must feed a same-size Conv2d')
+            i += 1
+            continue
+        if n in ('Conv2d', 'ConvTranspose2d'):
+            k = m.kernel_size[0]
+            if n == 'Conv2d':
+                padded = i > 0 and type(children[i - 1]).__name__ == 'ReplicationPad2d'
+                if k > 1 and not padded:
+                    raise NotImplementedError('un-padded k>1 Conv2d does not occur in AIVC')
+                kind, stride = 0, m.stride[0]
+            else:
+                if m.stride[0] != 2 or m.output_padding[0] != 1 or m.padding[0] != (k + 1) // 2 - 1:
+                    raise NotImplementedError('ConvTranspose2d geometry other than AIVC\'s x2')
+                kind, stride = 1, 2
+            act, gdn = 'no', None
+            if i + 1 < len(children):
+                nxt = children[i + 1]
+                if type(nxt).__name__ == 'GDN':
+                    gdn = _gdn_params(nxt)
+                    act = 'gdn_inverse' if gdn[2] else 'gdn'
+                    i += 1
+                elif _act_of(nxt) is not None:
+                    act = _act_of(nxt)
+                    i += 1
+            x = g.conv(kind, k, stride, x, m.weight, m.bias, act, gdn)
+        else:
+            x = lower(m, x, g)
+        i += 1
+    return x
+
+
+def _fold(g, res=None, gate=None, post='none'):
+    s = g.stages[-1]
+    assert s.res is None and s.gate is None and s.post == 'none', 'epilogue already occupied'
+    s.res, s.gate, s.post = res, gate, post
+
+
+def lower(m, x, g):
+    n = type(m).__name__
+    if n == 'Sequential':
+        return _lower_seq(m, x, g)
+    if n in ('CustomConvLayer', 'UpscalingLayer'):
+        return _lower_seq(m.layers, x, g)
+    if n in ('Conv2d', 'ConvTranspose2d'):
+        return _lower_seq([m], x, g)
+    if n == 'ChengResBlock':
+        if m.mode == 'plain':
+            skip = x
+        else:
+            skip = lower(m.aux_layer, x, g)
+        y = _lower_seq(m.layers, x, g)
+        _fold(g, res=skip)
+        return y
+    if n == 'ResBlock':
+        y = _lower_seq(m.layers, x, g)
+        _fold(g, res=x, post='relu')
+        return y
+    if n == 'AttentionResBlock':
+        y = _lower_seq(m.layers, x, g)
+        _fold(g, res=x, post='leaky_relu')
+        return y
+    if n == 'SimplifiedAttention':
+        trunk = _lower_seq(m.trunk, x, g)
+        y = _lower_seq(m.attention, x, g)
+        _fold(g, res=x, gate=trunk)
+        return y
+    if n == 'GDN':
+        raise NotImplementedError('stand-alone GDN: wrap it with its producing conv')
+    raise NotImplementedError('aivc_b200.plan: cannot lower ' + n)
+
+
+class Plan:
+    """Executable lowering of one transform for a fixed input size.
+
+    ``src``: T describing the input (its buffer may be supplied by the caller so that several
+    producers fill channel slices of one pixel-interleaved tensor).  ``dst_into``: optional
+    (Buffer, c_off) the last stage writes into (concat for free)."""
+
+    def __init__(self, module, h, w, cin, device, cfg=DEFAULT, src_buf=None, src_c_off=0,
+                 dst_into=None, out_scale=None, out_post='none', in_dtype=None):
+        self.cfg, self.device = cfg, torch.device(device)
+        g = Graph()
+        self.src = T(h, w, cin, external=True)
+        self.dst = lower(module, self.src, g)
+        self.stages = g.stages
+        if not self.stages:
+            raise ValueError('nothing to run')
+        last = self.stages[-1]
+        if out_scale is not None:
+            last.out_scale = out_scale.detach().float().reshape(-1)
+        if out_post != 'none':
+            assert last.post == 'none'
+            last.post = out_post
+        self._choose_engines()
+        self._assign_buffers(src_buf, src_c_off, dst_into, in_dtype)
+        self._materialize()
+
+    # -- engine / dtype / border selection
+    def _choose_engines(self):
+        tc = self.cfg.precision == 'bf16'
+        for s in self.stages:
+            cin, cout = s.src.c, s.dst.c
+            ok = tc and cin % self.cfg.tc_min_cin == 0 and cout % 16 == 0 and cout <= 256
+            if s.gdn is not None and cout > 128:
+                ok = False
+            s.engine = ENGINE_TC if ok else ENGINE_SIMT
+        for s in self.stages:
+            if s.engine == ENGINE_TC:
+                s.src.dtype = BF16
+                if s.kind == 0 and s.k > 1:
+                    s.src.pad = max(s.src.pad, s.k // 2)
+
+    def _assign_buffers(self, src_buf, src_c_off, dst_into, in_dtype):
+        for i, s in enumerate(self.stages):
+            for t in (s.src, s.res, s.gate):
+                if t is not None:
+                    t.last = max(t.last, i)
+            s.dst.first = i
+            s.dst.last = max(s.dst.last, i)
+        if src_buf is not None:
+            self.src.buf, self.src.c_off = src_buf, src_c_off
+            if self.src.dtype != src_buf.dtype or src_buf.pad < self.src.pad:
+                raise ValueError('supplied input buffer has dtype %d pad %d, plan needs dtype %d pad %d'
+                                 % (src_buf.dtype, src_buf.pad, self.src.dtype, self.src.pad))
+        else:
+            if in_dtype is not None and self.src.dtype == F32:
+                self.src.dtype = in_dtype
+            self.src.buf = Buffer(self.src.h, self.src.w, self.src.c, self.src.pad, self.src.dtype,
+                                  self.device)
+        self.dst.last = 10 ** 9
+        if dst_into is not None:
+            buf, off = dst_into
+            if (buf.h, buf.w) != (self.dst.h, self.dst.w):
+                raise ValueError('dst_into size mismatch')
+            self.dst.buf, self.dst.c_off, self.dst.dtype, self.dst.pad = buf, off, buf.dtype, buf.pad
+        free, self.buffers = {}, []
+        for i, s in enumerate(self.stages):
+            t = s.dst
+            if t.buf is None:
+                key = (t.h, t.w, t.c, t.pad, t.dtype)
+                pool = free.setdefault(key, [])
+                t.buf = pool.pop() if pool else Buffer(t.h, t.w, t.c, t.pad, t.dtype, self.device)
+                if t.buf not in self.buffers:
+                    self.buffers.append(t.buf)
+            # release tensors whose last reader is this stage (never the one just written)
+            for u in {id(x): x for x in (s.src, s.res, s.gate) if x is not None}.values():
+                if u.last == i and not u.external and u is not self.dst and u.buf is not None \
+                        and u.c_off == 0 and u.c == u.buf.c:
+                    free.setdefault((u.h, u.w, u.c, u.pad, u.dtype), []).append(u.buf)
+
+    def _materialize(self):
+        L = _lib.lib()
+        dev = self.device
+        n = len(self.stages)
+        self.ops = (ConvOp * n)()
+        self._keep = []
+        st = _lib.stream_ptr()
+        for i, s in enumerate(self.stages):
+            op = self.ops[i]
+            cin, cout = s.src.c, s.dst.c
+            op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
+            op.inp, op.out = s.src.fmap(), s.dst.fmap()
+            wsrc = s.weight.to(dev, torch.float32).contiguous()
+            cin_pad, cout_pad = cin, cout
+            nbytes = L.aivc_packed_weight_bytes(s.k, cin, cout, s.engine, cin_pad, cout_pad)
+            wdst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.aivc_pack_conv_weight(wsrc.data_ptr(), wdst.data_ptr(), s.kind, s.k, cin, cout,
+                                               s.engine, cin_pad, cout_pad, st))
+            op.weight = wdst.data_ptr()
+            self._keep += [wsrc, wdst]
+            if s.bias is not None:
+                b = s.bias.to(dev, torch.float32).contiguous()
+                op.bias = b.data_ptr()
+                self._keep.append(b)
+            op.act, op.post = ACT[s.act], POST[s.post]
+            if s.gdn is not None:
+                beta, gamma, _ = s.gdn
+                beta = beta.to(dev).contiguous()
+                if s.engine == ENGINE_SIMT:
+                    gm = gamma.to(dev).t().contiguous()                 # [j][i]
+                    scratch = torch.empty(cout * s.dst.h * s.dst.w, dtype=torch.float32, device=dev)
+                    op.scratch = scratch.data_ptr()
+                    self._keep.append(scratch)
+                else:
+                    gm = gamma.to(dev).to(torch.bfloat16).contiguous()  # [i][j], K-major B operand
+                op.gdn_beta, op.gdn_gamma = beta.data_ptr(), gm.data_ptr()
+                self._keep += [beta, gm]
+            if s.res is not None:
+                op.residual = s.res.fmap()
+            if s.gate is not None:
+                op.gate = s.gate.fmap()
+            if s.out_scale is not None:
+                sc = s.out_scale.to(dev, torch.float32).contiguous()
+                op.out_scale = sc.data_ptr()
+                self._keep.append(sc)
+        torch.cuda.current_stream().synchronize()
+
+    @property
+    def in_fmap(self):
+        return self.src.fmap()
+
+    @property
+    def out_fmap(self):
+        return self.dst.fmap()
+
+    def run(self):
+        L = _lib.lib()
+        _lib.check(L.aivc_conv2d_fused_seq(self.ops, len(self.ops), _lib.stream_ptr()))
+
+    def flops(self):
+        """Algorithmic FLOPs of the reference graph: convs, tconvs and GDN 1x1."""
+        f = 0
+        for s in self.stages:
+            px = s.dst.h * s.dst.w if s.kind == 0 else s.src.h * s.src.w
+            f += 2 * s.k * s.k * s.src.c * s.dst.c * px
+            if s.gdn is not None:
+                f += 2 * s.dst.c * s.dst.c * s.dst.h * s.dst.w
+        return f
+
+
+# ------------------------------------------------------------------ nn.Module boundary
+_CACHE_ATTR = '_aivc_b200_plans'
+
+
+def run_module(module, x, cfg=DEFAULT):
+    """forward() of the drop-in classes: NCHW fp32 CUDA tensor in, NCHW fp32 tensor out."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError('aivc_b200 layers run on a CUDA device only (no CPU fallback); got '
+                           + str(getattr(x, 'device', type(x))))
+    if x.dim() != 4 or x.shape[0] != 1:
+        raise ValueError('expected a [1, C, H, W] tensor (AIVC codes one frame at a time)')
+    L = _lib.lib()
+    x = x.contiguous().float()
+    _, c, h, w = x.shape
+    cache = module.__dict__.setdefault(_CACHE_ATTR, {})
+    key = (h, w, c, x.device.index, cfg.key())
+    plan = cache.get(key)
+    if plan is None:
+        with torch.cuda.device(x.device):
+            plan = Plan(module, h, w, c, x.device, cfg)
+        cache[key] = plan
+    with torch.cuda.device(x.device):
+        st = _lib.stream_ptr()
+        fin = plan.in_fmap
+        _lib.check(L.aivc_nchw_to_fmap(x.data_ptr(), C.byref(fin), st))
+        plan.run()
+        fout = plan.out_fmap
+        out = torch.empty((1, fout.c, fout.h, fout.w), dtype=torch.float32, device=x.device)
+        _lib.check(L.aivc_fmap_to_nchw(C.byref(fout), out.data_ptr(), st))
+    return out

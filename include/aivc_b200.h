@@ -1,0 +1,182 @@
+/* aivc_b200 -- C ABI of the B200-native AIVC hot path (libaivc_b200.so).
+ *
+ * The reference (Orange-OpenSource/AIVC) has no FFI: its hot path is Python classes
+ * calling torch.nn.functional.  This header is the boundary a maintainer binds with
+ * ctypes; each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; device pointers unless noted "host".
+ *   - every device entry point is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), performs no allocation and no hidden synchronisation; the caller owns all
+ *     buffers, including outputs and scratch.
+ *   - return value 0 = ok, non-zero = error; aivc_last_error() gives the (thread-local)
+ *     message.  Nothing throws or exits across the ABI.
+ *   - feature maps are NHWC ("pixel-major") with an optional replicate-filled border so
+ *     that 3x3/5x5 taps of the next convolution are plain in-bounds TMA box loads.
+ */
+#ifndef AIVC_B200_H
+#define AIVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIVC_ABI_VERSION 1
+
+/* ---- data types / enums ------------------------------------------------------------ */
+enum { AIVC_F32 = 0, AIVC_BF16 = 1 };
+
+/* activation applied right after bias (custom_conv_layers.py:155-177, attention.py:82) */
+enum {
+    AIVC_ACT_NONE = 0,
+    AIVC_ACT_LEAKY = 1,    /* LeakyReLU(0.01) */
+    AIVC_ACT_RELU = 2,
+    AIVC_ACT_SIGMOID = 3,
+    AIVC_ACT_GDN = 4,      /* x * (beta + gamma.x^2)^-1/2   misc_layers.py:113-154 */
+    AIVC_ACT_IGDN = 5      /* x * (beta + gamma.x^2)^+1/2 */
+};
+
+/* applied last, after gate/residual */
+enum {
+    AIVC_POST_NONE = 0,
+    AIVC_POST_LEAKY = 1,       /* AttentionResBlock: leaky(x + f(x))  attention.py:41 */
+    AIVC_POST_RELU = 2,        /* ResBlock: relu(x + f(x))            custom_conv_layers.py:126 */
+    AIVC_POST_ROUND_CLAMP = 3  /* Quantizer at eval + AC range clamp  misc_layers.py:167 */
+};
+
+enum { AIVC_ENGINE_SIMT = 0, AIVC_ENGINE_TC = 1 };
+
+/* A view on an NHWC feature map living in a (possibly wider, possibly bordered) buffer.
+ * element (y, x, ch) of the view is at
+ *   data[ ((y + pad) * pitch + (x + pad)) * c_stride + c_off + ch ]
+ * `pad` border pixels on every side hold replicated edge values (written by producers). */
+typedef struct {
+    void *data;
+    int32_t h, w;        /* logical size */
+    int32_t c;           /* channels in this view */
+    int32_t c_off;       /* first channel of the view inside a pixel */
+    int32_t c_stride;    /* channels allocated per pixel */
+    int32_t pad;         /* border width */
+    int32_t pitch;       /* allocated pixels per row  (>= w + 2*pad) */
+    int32_t rows;        /* allocated rows            (>= h + 2*pad) */
+    int32_t dtype;       /* AIVC_F32 | AIVC_BF16 */
+    int32_t _r;
+} aivc_fmap;
+
+/* One fused convolution stage.
+ *   kind 0: replicate-pad(k/2) + Conv2d(k, stride)      CustomConvLayer  custom_conv_layers.py:129-180
+ *           (also the bare 1x1 Conv2d's of ChengResBlock/attention: pad 0)
+ *   kind 1: ConvTranspose2d(k, stride 2, pad (k+1)/2-1, output_padding 1)
+ *                                                        UpscalingLayer   custom_conv_layers.py:183-253
+ *   out = post( act(conv(in) + bias) * gate + residual ) * out_scale
+ */
+typedef struct {
+    int32_t kind, k, stride, engine;
+    aivc_fmap in, out;
+    const void *weight;        /* packed by aivc_pack_conv_weight for the chosen engine */
+    const float *bias;         /* [cout] or NULL */
+    int32_t act, post;
+    const float *gdn_beta;     /* [cout], reparametrised */
+    const void *gdn_gamma;     /* [cout][cout] fp32 (SIMT) or bf16 K-major (TC) */
+    aivc_fmap residual;        /* .data == NULL -> none */
+    aivc_fmap gate;            /* .data == NULL -> none */
+    const float *out_scale;    /* [cout] or NULL: GainMatrix 'enc' folded in (gain_matrix.py:122-124) */
+    void *scratch;             /* SIMT GDN needs cout*h*w floats; else NULL */
+    int32_t act_channels;      /* `act` applies to output channels [0, act_channels); 0 = all */
+    int32_t _r;
+} aivc_conv_op;
+
+/* ---- library ----------------------------------------------------------------------- */
+int aivc_abi_version(void);
+const char *aivc_last_error(void);
+
+/* ---- convolution stack ------------------------------------------------------------- */
+/* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or
+ * ConvTranspose2d [cin][cout][k][k] fp32 (device).  dst: SIMT [k*k][cin][cout] fp32,
+ * TC [k*k][cout_pad][cin_pad] bf16.  Returns bytes written through *dst_bytes. */
+int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin, int cout,
+                          int engine, int cin_pad, int cout_pad, void *stream);
+size_t aivc_packed_weight_bytes(int k, int cin, int cout, int engine, int cin_pad, int cout_pad);
+
+int aivc_conv2d_fused(const aivc_conv_op *op, void *stream);
+/* run n stages back to back on one stream (one FFI crossing per transform) */
+int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream);
+
+/* ---- layout bridges at the nn.Module boundary (NCHW fp32 <-> bordered NHWC) --------- */
+int aivc_nchw_to_fmap(const float *src, const aivc_fmap *dst, void *stream);
+int aivc_fmap_to_nchw(const aivc_fmap *src, float *dst, void *stream);
+int aivc_fill_border(const aivc_fmap *m, void *stream);
+
+/* ---- pixel ends -------------------------------------------------------------------- */
+/* InputLayer (ae_layers.py:27-35): planar 4:2:0 -> 3 channels of `dst` (Y, nearest-x2 U, V).
+ * planes are uint8 (levels/255) when u8 != 0, else fp32 in [0,1]. */
+int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, const aivc_fmap *dst,
+                        void *stream);
+
+/* MOFNetDecoder post-processing + motion compensation + alpha split
+ * (decode.py:729-739, 524-536; optical_flow.py:14-55).  mof: 6 channels (alpha, beta,
+ * v_prev xy, v_next xy).  frame_is_p: beta := 1, v_next := 0.
+ * pred = alpha * x_warp (3 ch), skip = (1 - alpha) * x_warp (3 ch). */
+int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
+                    int frame_is_p, const aivc_fmap *pred, const aivc_fmap *skip, void *stream);
+/* stand-alone motion compensation for the drop-in MotionCompensation module:
+ * all tensors NCHW fp32, beta [3][h][w], flows [2][h][w]. */
+int aivc_warp_blend_nchw(const float *prev, const float *next, const float *v_prev,
+                         const float *v_next, const float *beta, float *out, int h, int w,
+                         void *stream);
+
+/* x = codec (+ skip); OutputLayer (ae_layers.py:42-56) + crop / U,V replicate-pad
+ * (decode.py:557-571) + cast_before_png_saving (img_processing.py:68-73).
+ * Writes uint8 planes y[h][w], u,v[ceil(h/2)][ceil(w/2)] and (optionally) the 4:4:4
+ * fp32 reference feature map the next frames read (InputLayer of the result). */
+int aivc_finalize_frame(const aivc_fmap *codec, const aivc_fmap *skip, uint8_t *y, uint8_t *u,
+                        uint8_t *v, const aivc_fmap *ref444, void *stream);
+
+/* ---- hyperprior / quantisation ----------------------------------------------------- */
+/* PdfParamParameterizer (misc_layers.py:180-269): hs [2C] -> mu, sigma NCHW fp32. */
+int aivc_mu_sigma_nchw(const float *hs, float *mu, float *sigma, int c, int hw, void *stream);
+
+/* Encoder side, one latent (replaces PdfParamParameterizer + Quantizer + get_y_cdf +
+ * torchac's float->int16 conversion; misc_layers.py:167,180-269, bitstream.py:127-154,241-255).
+ *   y      : C channels, already multiplied by the encoder gain
+ *   hs     : 2C channels (mu | log-variance), at least h x w
+ *   q      : int16 NCHW [C][h][w]            = clamp(round(y - mu), -256, 255)
+ *   bounds : uint32 NCHW, c_low | c_high<<16 = 16-bit CDF bounds of q under Laplace(0, sigma/sqrt 2)
+ *   nz     : int32 [C], set to 1 where the channel has a non-zero symbol (zero it first)
+ *   yhat   : C channels = (q + mu) * dec_gain   (input of g_s; decode.py:867-885)
+ */
+int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *dec_gain,
+                         int16_t *q, uint32_t *bounds, int32_t *nz, const aivc_fmap *yhat,
+                         void *stream);
+/* Decoder side: scale b = sigma/sqrt(2) per symbol, fp32 NCHW, for the host range decoder. */
+int aivc_laplace_scale(const aivc_fmap *hs, int c, float *b, void *stream);
+/* Decoder side: yhat = (q + mu) * dec_gain from host-decoded symbols. */
+int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *dec_gain,
+                           const aivc_fmap *yhat, void *stream);
+/* z symbols <-> feature map (values already rounded by the h_a epilogue). */
+int aivc_fmap_to_i16(const aivc_fmap *src, int16_t *dst, void *stream);
+int aivc_i16_to_fmap(const int16_t *src, const aivc_fmap *dst, void *stream);
+
+/* ---- range coder (host; replaces torchac as called at bitstream.py:281,454,482) ------ */
+/* All pointers are HOST memory.  Output capacity must be >= aivc_rc_bound(n). */
+size_t aivc_rc_bound(size_t n_symbols);
+/* symbols given by their 16-bit CDF bounds (c_low | c_high << 16), coded in array order */
+int aivc_rc_encode_bounds(const uint32_t *bounds, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+/* 'pmf' mode: per-channel table [c][514] uint16, symbols int16 in [-256, 255], NCHW order */
+int aivc_rc_encode_table(const uint16_t *table, const int16_t *sym, int c, size_t hw, uint8_t *out,
+                         size_t cap, size_t *out_len);
+int aivc_rc_decode_table(const uint16_t *table, const uint8_t *in, size_t in_len, int c, size_t hw,
+                         int16_t *sym);
+/* 'laplace' mode: per-symbol scale b (from aivc_laplace_scale), symbols out in [-256, 255] */
+int aivc_rc_decode_laplace(const float *b, const uint8_t *in, size_t in_len, size_t n, int16_t *sym);
+/* host evaluation of the integer Laplace CDF (same arithmetic as the device) */
+uint32_t aivc_laplace_cdf_int_host(float b, int i);
+float aivc_sigma_from_logvar_host(float v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIVC_B200_H */

@@ -1,0 +1,162 @@
+"""CPU suite: host-side product logic (range coder, framing, GOP schedules, lowering) and the
+C-ABI surface.  No compute kernel is launched."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from aivc_b200 import _lib, entropy, gop as G, plan as P
+from oracle import codec_ref as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'aivc_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(aivc_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), 'missing export ' + name
+    assert declared == set(_lib.EXPORTS)
+    assert _lib.lib().aivc_abi_version() == 1
+
+
+def _enc_bounds(bounds):
+    L = _lib.lib()
+    out = np.empty(L.aivc_rc_bound(bounds.size), np.uint8)
+    n = C.c_size_t()
+    _lib.check(L.aivc_rc_encode_bounds(bounds.ctypes.data, bounds.size, out.ctypes.data, out.size, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def test_rangecoder_known_answers():
+    """Hand-derived: with a uniform 2-symbol CDF {0, 32768, 65536} every symbol is one bit
+    (0 -> '0', 1 -> '1'), followed by the terminating '01' / '10' pattern and zero padding."""
+    half = np.uint32(0 | (32768 << 16))          # symbol 0: [0, 32768)
+    # eight zeros: after 8 settled '0' bits low = 0 -> final bit 0 + one pending 1  => 00000000 01
+    assert _enc_bounds(np.array([half] * 8, np.uint32)) == bytes([0x00, 0x40])
+    # empty message: low = 0 -> '0' then pending '1'
+    assert _enc_bounds(np.zeros(0, np.uint32)) == bytes([0x40])
+    # oracle coder agrees on both
+    assert O.rc_encode_bounds([0] * 8, [32768] * 8) == bytes([0x00, 0x40])
+    assert O.rc_encode_bounds([], []) == bytes([0x40])
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_rangecoder_matches_oracle_and_roundtrips(seed):
+    rng = np.random.default_rng(seed)
+    L = _lib.lib()
+    n = int(rng.integers(1, 4000))
+    sig = np.exp(rng.uniform(-7, 4.5, n)).astype(np.float32)
+    q = np.clip(np.rint(rng.laplace(0, sig / np.sqrt(2))), -256, 255).astype(np.int16)
+    if seed == 0:
+        q[:] = 0
+    if seed == 1:
+        q[::7] = 255
+        q[3::7] = -256
+    table = O.laplace_table_spec(sig)
+    ar = np.arange(n)
+    lo = table[ar, q.astype(int) + 256].astype(np.uint32)
+    hi = table[ar, q.astype(int) + 257].astype(np.uint32)
+    ours = _enc_bounds(lo | (hi << 16))
+    assert ours == O.rc_encode_table(table, (q + 256).astype(np.int16))
+    b = (sig / np.float32(1.41421354)).astype(np.float32)
+    dec = np.empty(n, np.int16)
+    buf = np.frombuffer(ours, np.uint8)
+    _lib.check(L.aivc_rc_decode_laplace(b.ctypes.data, buf.ctypes.data, len(ours), n, dec.ctypes.data))
+    assert np.array_equal(dec, q)
+    assert np.array_equal(O.rc_decode_table(table, ours, n) - 256, q)
+
+
+def test_host_cdf_equals_oracle_spec():
+    rng = np.random.default_rng(3)
+    L = _lib.lib()
+    sig = np.exp(rng.uniform(-9.3, 5.1, 300)).astype(np.float32)
+    table = O.laplace_table_spec(sig)
+    b = (sig / np.float32(1.41421354)).astype(np.float32)
+    for j in range(sig.size):
+        for i in (0, 1, 128, 250, 255, 256, 257, 258, 300, 512, 513):
+            assert L.aivc_laplace_cdf_int_host(float(b[j]), i) == table[j, i]
+
+
+def test_sigma_host_close_to_torch():
+    v = torch.linspace(-25, 15, 4001)
+    ref = torch.exp(0.5 * torch.clamp(v, -18.4207, 10.0)).numpy()
+    L = _lib.lib()
+    got = np.array([L.aivc_sigma_from_logvar_host(float(x)) for x in v.numpy()], np.float32)
+    assert np.max(np.abs(got - ref) / ref) < 2.5e-7        # <= 2 ulp of torch's vectorised expf
+
+
+def test_latent_framing_roundtrip():
+    rng = np.random.default_rng(5)
+    c, h, w = 8, 5, 7
+    sig = np.exp(rng.uniform(-1, 2, (c, h, w))).astype(np.float32)
+    q = np.clip(np.rint(rng.laplace(0, sig)), -256, 255).astype(np.int16)
+    q[[1, 4]] = 0
+    b = (sig / np.float32(1.41421354)).astype(np.float32)
+    L = _lib.lib()
+    bounds = np.empty((c, h * w), np.uint32)
+    for ch in range(c):
+        for i in range(h * w):
+            s = int(q[ch].reshape(-1)[i]) + 256
+            bb = float(b[ch].reshape(-1)[i])
+            bounds[ch, i] = L.aivc_laplace_cdf_int_host(bb, s) | (L.aivc_laplace_cdf_int_host(bb, s + 1) << 16)
+    nz = (np.abs(q).reshape(c, -1).sum(1) != 0).astype(np.int32)
+    sec = entropy.encode_y(bounds, nz)
+    n = int.from_bytes(sec[:4], 'big')
+    assert n == len(sec) - 4 and sec[4] == 6 and list(sec[5:11]) == [0, 2, 3, 5, 6, 7]
+    assert np.array_equal(entropy.decode_y(sec[4:], b, c, h, w), q)
+    # same bytes as the oracle's framing of the same latent
+    ref = O.ac_encode_latent(torch.from_numpy(q.astype(np.float32))[None], 'laplace',
+                             sigma=torch.from_numpy(sig)[None], cdf_mode='spec')
+    assert ref == sec
+    # z / pmf mode
+    from aivc_b200.layers import BallePdfEstim
+    torch.manual_seed(0)
+    pz = BallePdfEstim(4, '')
+    tab = entropy.z_table_u16(pz)
+    assert np.array_equal(tab, O.z_table_u16(pz))
+    z = rng.integers(-6, 7, (4, 3, 2)).astype(np.int16)
+    sz = entropy.encode_z(tab, z)
+    assert sz == O.ac_encode_latent(torch.from_numpy(z.astype(np.float32))[None], 'pmf', z_table=tab)
+    assert np.array_equal(entropy.decode_z(tab, sz[4:], 4, 3, 2), z)
+    secs = entropy.split_sections((0).to_bytes(4, 'big') * 2 + sz + sec)
+    assert secs[0] == b'' and secs[1] == b'' and secs[2] == sz[4:] and secs[3] == sec[4:]
+
+
+def test_gop_levels():
+    g = G.generate_gop_struct('1_GOP_32')
+    assert [len(l) for l in G.levels(g)] == [1, 1, 1, 2, 4, 8, 16]
+    assert G.coding_order(g)[:7] == ['frame_%d' % i for i in (0, 32, 16, 8, 4, 2, 1)]
+    g = G.generate_gop_struct('LDP_8')
+    assert [len(l) for l in G.levels(g)] == [1] * 9
+
+
+def test_lowering_fuses_blocks():
+    import aivc_b200.layers as M
+    g = P.Graph()
+    x = P.T(32, 48, 16, external=True)
+    y = P.lower(M.ChengResBlock(16, 'down'), x, g)
+    assert (y.h, y.w, y.c) == (16, 24, 16)
+    assert [(s.k, s.stride, s.act) for s in g.stages] == [(1, 2, 'no'), (3, 2, 'leaky_relu'), (3, 1, 'gdn')]
+    assert g.stages[2].res is g.stages[0].dst
+    g = P.Graph()
+    y = P.lower(M.SimplifiedAttention(16), x, g)
+    assert len(g.stages) == 13
+    last = g.stages[-1]
+    assert last.act == 'sigmoid' and last.gate is g.stages[5].dst and last.res is x
+    assert all(s.post == 'relu' for i, s in enumerate(g.stages[:12]) if i % 2 == 1)
+    g = P.Graph()
+    y = P.lower(M.ChengResBlock(16, 'up_tconv'), x, g)
+    assert (y.h, y.w) == (64, 96) and [s.kind for s in g.stages] == [1, 1, 0]
+
+
+def test_layers_refuse_cpu():
+    import aivc_b200.layers as M
+    with pytest.raises(RuntimeError):
+        M.CustomConvLayer(3, 4, 4)(torch.zeros(1, 4, 8, 8))

@@ -1,0 +1,65 @@
+"""CPU suite: the oracle against the committed golden vectors (which gen_golden.py pinned to
+the reference classes), without /root/reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_ref as R, codec_ref as C
+from tests.leafcfg import LEAVES, load_leaf
+
+
+@pytest.mark.parametrize('name', sorted(LEAVES))
+def test_oracle_reproduces_leaf_golden(name, golden_dir):
+    m, fx = load_leaf(name, golden_dir)
+    with torch.no_grad():
+        for i in range(2):
+            y = R.forward_module(m, torch.from_numpy(fx['x%d' % i]))
+            assert torch.equal(y, torch.from_numpy(fx['y%d' % i]))
+
+
+def test_oracle_pixel_ends(golden_dir):
+    fx = np.load(os.path.join(golden_dir, 'misc.npz'))
+    for tag in ('even', 'odd'):
+        yuv = {k: torch.from_numpy(fx['%s_in_%s' % (tag, k)]) for k in 'yuv'}
+        x444 = R.input_layer(yuv)
+        assert torch.equal(x444, torch.from_numpy(fx[tag + '_x444']))
+        h, w = x444.shape[2:]
+        fin = R.finalize_frame(x444 * 1.3 - 0.1, h, w)
+        for k in 'yuv':
+            assert torch.equal(fin[k], torch.from_numpy(fx['%s_fin_%s' % (tag, k)]))
+        wr = R.warp(x444, torch.from_numpy(fx[tag + '_flow']))
+        assert torch.equal(wr, torch.from_numpy(fx[tag + '_warp']))
+    mu, sigma = R.mu_sigma(torch.from_numpy(fx['hs_out']), 8)
+    assert torch.equal(mu, torch.from_numpy(fx['mu'])) and torch.equal(sigma, torch.from_numpy(fx['sigma']))
+
+
+def test_laplace_spec_matches_torch_reference_table(golden_dir):
+    """The deterministic integer Laplace CDF vs the table the reference builds with torch fp32."""
+    fx = np.load(os.path.join(golden_dir, 'misc.npz'))
+    spec = C.laplace_table_spec(fx['laplace_sigma'])
+    ref = fx['laplace_ref_u16']
+    d = np.abs(spec.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1
+    assert (d != 0).mean() < 1e-3
+    # strictly increasing rows, as the range coder needs (entry 513 wraps to 0 and is never
+    # read: the coder substitutes 0x10000 for the top symbol)
+    assert (np.diff(spec[:, :513].astype(np.int32), axis=1) > 0).all()
+
+
+def test_system_golden_decodes(golden_dir):
+    """Oracle decoder on the committed bitstreams reproduces the committed reconstruction."""
+    from aivc_b200 import models, gop as G
+    fx = np.load(os.path.join(golden_dir, 'system_80x112.npz'))
+    h, w = int(fx['H']), int(fx['W'])
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    tables = C.Tables(net)
+    gop = G.generate_gop_struct('1_GOP_2')
+    for mode in ('spec', 'reference'):
+        bts = {f: fx['%s_bytes_%s' % (mode, f)].tobytes() for f in gop}
+        rec = C.decode_gop(net, tables, bts, gop, h, w, cdf_mode=mode)
+        for f in gop:
+            for k in 'yuv':
+                got = (rec[f][k].numpy() * 255).round().astype(np.uint8)
+                assert np.array_equal(got, fx['%s_rec_%s_%s' % (mode, f, k)])
