@@ -1,5 +1,595 @@
+// tcgen05 implicit-GEMM convolution / transposed convolution for sm_100a.
+//
+//   D[128 pixels x N channels] (fp32, TMEM) += A[128 x BK] (bf16, smem) . B[N x BK]^T (bf16, smem)
+//
+// * A tiles are *not* gathered: the producing kernel wrote the activation as bordered NHWC, so
+//   tap (ky,kx) of a TH x TW pixel tile is one TMA box load at a shifted origin -- a 3-D map
+//   for stride 1 and transposed-conv phases, a 5-D (c, x parity, x/2, y parity, y/2) map for
+//   stride 2.  Out-of-range rows/columns of partial tiles (and the zero padding of transposed
+//   convs) come from TMA's zero fill.
+// * B tiles come from weights packed [tap][cout][cin] (K-major).
+// * warp 0 = TMA producer, warp 1 = TMEM allocator + tcgen05.mma issuer, warps 2-5 = epilogue
+//   (tcgen05.ld 32 lanes x 16 columns at a time): bias, LeakyReLU/ReLU/sigmoid, gate, residual,
+//   post activation, per-channel gain, bf16/fp32 store incl. the replicate border.
+// * GDN/IGDN is chained on the TMEM-resident tile: the epilogue squares the tile into a
+//   swizzled smem A operand, a second tcgen05.mma multiplies it with gamma (smem B operand,
+//   TMA-loaded) into a second TMEM region, and the final pass reads both accumulators.
+//
+// Replaces CustomConvLayer / UpscalingLayer / GDN forward
+// (layers/misc/custom_conv_layers.py:129-253, layers/misc/misc_layers.py:113-154).
+#include <cuda.h>
 #include "common.cuh"
+
+namespace {
+
+constexpr int MAX_TAPS = 25;
+constexpr int NTHREADS = 192;
+constexpr int NSTAGES = 3;
+
+struct Phase {
+    int ntaps, out_py, out_px, _pad;
+    signed char ax[MAX_TAPS], ay[MAX_TAPS];      // origin offsets (already include border / parity shift)
+    unsigned char qx[MAX_TAPS], qy[MAX_TAPS];    // parities for the 5-D (stride-2) map
+    unsigned char widx[MAX_TAPS];
+};
+
+struct TcParams {
+    FMap out, res, gate;
+    const float *bias, *gdn_beta, *out_scale;
+    int cout, kchunks;
+    int act, post, act_channels, gdn;            // gdn: 0 none, 1 divide, 2 multiply
+    int tw, th, tiles_x;
+    int mh, mw, out_step, mode;                  // mode 0: 3-D map, 1: 5-D map
+    int tmem_cols, kg;                           // kg: columns per swizzle atom of the GDN operands
+    uint32_t stage_bytes, a_bytes, b_bytes;
+    Phase ph[4];
+};
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    const long long t0 = clock64();
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();   // never hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand descriptor: `rowbytes` = bytes of one row (= swizzle span: 128 / 64 / 32)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int rowbytes) {
+    const uint64_t layout = rowbytes == 128 ? 2ull : (rowbytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (uint64_t)(8 * rowbytes) >> 4;       // 8-row core-matrix group stride
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    // c = f32 (1<<4), a = b = bf16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ epilogue IO
+struct VecInfo {
+    bool vec;       // 16-channel groups are 16-byte aligned
+};
+__device__ __forceinline__ bool fmap_vec_ok(const FMap &m) {
+    const int al = (m.dtype == AIVC_F32) ? 4 : 8;
+    return (m.c_off % al == 0) && (m.c_stride % al == 0) && (((uintptr_t)m.data & 15) == 0);
+}
+
+__device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, int ch0, int nvalid, float *v) {
+    const size_t base = fm_index(m, y, x, ch0);
+    if (vec && nvalid == 16) {
+        if (m.dtype == AIVC_F32) {
+            const float4 *p = reinterpret_cast<const float4 *>((const float *)m.data + base);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 t = p[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else {
+            const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + base);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint4 t = p[i];
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+                    v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < 16; ++i) v[i] = (i < nvalid) ? fm_load(m, y, x, ch0 + i) : 0.f;
+    }
+}
+
+__device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, int ch0, int nvalid,
+                                        const float *v) {
+    const int p = m.pad;
+    const int y0 = (y == 0) ? 0 : y + p, y1 = (y == m.h - 1) ? y + 2 * p : y + p;
+    const int x0 = (x == 0) ? 0 : x + p, x1 = (x == m.w - 1) ? x + 2 * p : x + p;
+    if (vec && nvalid == 16) {
+        if (m.dtype == AIVC_F32) {
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    float4 *q = reinterpret_cast<float4 *>(
+                        (float *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+        } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+            }
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    uint4 *q = reinterpret_cast<uint4 *>(
+                        (__nv_bfloat16 *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
+                    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+        }
+    } else {
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx)
+                for (int i = 0; i < nvalid; ++i) fm_store_raw(m, yy, xx, ch0 + i, v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ kernel
+template <int BK>
+__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmG,
+                                                           const TcParams p) {
+    constexpr int ROWB = BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[NSTAGES], bar_empty[NSTAGES], bar_acc, bar_gamma, bar_xsq, bar_norm;
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t *tiles = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *xsq_tile = tiles + NSTAGES * p.stage_bytes;                 // [chunks][128][kg] bf16
+    uint8_t *gam_tile = xsq_tile + 128 * p.cout * 2;                     // [chunks][N][kg] bf16
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const Phase &ph = p.ph[blockIdx.z];
+    const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x % p.tiles_x;
+    const int my0 = tile_y * p.th, mx0 = tile_x * p.tw;
+    const int N = p.cout;
+    const int total_it = ph.ntaps * p.kchunks;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_acc, 1);
+        mbar_init(&bar_gamma, 1);
+        mbar_init(&bar_xsq, 128);
+        mbar_init(&bar_norm, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_slot)),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            if (p.gdn) {
+                const int chunks = N / p.kg;
+                mbar_expect_tx(&bar_gamma, (uint32_t)(N * N * 2));
+                for (int c = 0; c < chunks; ++c)
+                    tma_load_2d(gam_tile + (size_t)c * N * p.kg * 2, &tmG, &bar_gamma, c * p.kg, 0);
+            }
+            int it = 0;
+            for (int t = 0; t < ph.ntaps; ++t) {
+                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                    const int s = it % NSTAGES;
+                    const uint32_t par = (uint32_t)((it / NSTAGES) & 1);
+                    mbar_wait(&bar_empty[s], par ^ 1u);
+                    uint8_t *a_dst = tiles + (size_t)s * p.stage_bytes;
+                    uint8_t *b_dst = a_dst + p.a_bytes;
+                    mbar_expect_tx(&bar_full[s], p.a_bytes + p.b_bytes);
+                    if (p.mode == 0)
+                        tma_load_3d(a_dst, &tmA, &bar_full[s], kc * BK, mx0 + ph.ax[t], my0 + ph.ay[t]);
+                    else
+                        tma_load_5d(a_dst, &tmA, &bar_full[s], kc * BK, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
+                                    my0 + ph.ay[t]);
+                    tma_load_3d(b_dst, &tmB, &bar_full[s], kc * BK, 0, ph.widx[t]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(N);
+            for (int it = 0; it < total_it; ++it) {
+                const int s = it % NSTAGES;
+                const uint32_t par = (uint32_t)((it / NSTAGES) & 1);
+                mbar_wait(&bar_full[s], par);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + (size_t)s * p.stage_bytes);
+                const uint64_t adesc = make_desc(a_addr, ROWB);
+                const uint64_t bdesc = make_desc(a_addr + p.a_bytes, ROWB);
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                              (it > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_acc);
+            if (p.gdn) {
+                // norm[128 x N] = xsq[128 x N] . gamma[N x N]^T   (second accumulator at column N)
+                mbar_wait(&bar_gamma, 0);
+                mbar_wait(&bar_xsq, 0);
+                tc_fence_after();
+                const int rowb = p.kg * 2;
+                for (int k16 = 0; k16 < N / 16; ++k16) {
+                    const int chunk = (k16 * 16) / p.kg, inner = (k16 * 16) % p.kg;
+                    const uint64_t ad = make_desc(smem_u32(xsq_tile + (size_t)chunk * 128 * rowb) + inner * 2, rowb);
+                    const uint64_t bd = make_desc(smem_u32(gam_tile + (size_t)chunk * N * rowb) + inner * 2, rowb);
+                    umma_bf16(tmem_base + (uint32_t)N, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+                }
+                umma_commit(&bar_norm);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;               // tile row = output pixel
+        const int my = my0 + row / p.tw, mx = mx0 + row % p.tw;
+        const int oy = my * p.out_step + ph.out_py, ox = mx * p.out_step + ph.out_px;
+        const bool valid = (my < p.mh) && (mx < p.mw) && (oy < p.out.h) && (ox < p.out.w);
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const bool out_vec = fmap_vec_ok(p.out);
+        const bool res_vec = p.res.data ? fmap_vec_ok(p.res) : false;
+        const bool gate_vec = p.gate.data ? fmap_vec_ok(p.gate) : false;
+
+        mbar_wait(&bar_acc, 0);
+        tc_fence_after();
+
+        if (p.gdn) {
+            // pass 1: (acc + bias)^2 -> bf16 A operand in smem (K-major, swizzled like TMA would)
+            const int rowb = p.kg * 2;
+            const int sw_bits = rowb == 128 ? 3 : (rowb == 64 ? 2 : 1);
+            for (int j0 = 0; j0 < N; j0 += 16) {
+                float v[16];
+                tmem_ld16(tlane + (uint32_t)j0, v);
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = v[2 * i] + p.bias[j0 + 2 * i], b = v[2 * i + 1] + p.bias[j0 + 2 * i + 1];
+                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(a * a, b * b);
+                    w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+                }
+                const int chunk = j0 / p.kg, inner = j0 % p.kg;
+                uint8_t *cbase = xsq_tile + (size_t)chunk * 128 * rowb;
+#pragma unroll
+                for (int hsel = 0; hsel < 2; ++hsel) {
+                    uint32_t off = (uint32_t)(row * rowb + inner * 2 + hsel * 16);
+                    off ^= ((off >> 7) & ((1u << sw_bits) - 1u)) << 4;
+                    *reinterpret_cast<uint4 *>(cbase + off) =
+                        make_uint4(w[4 * hsel], w[4 * hsel + 1], w[4 * hsel + 2], w[4 * hsel + 3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&bar_xsq);
+            mbar_wait(&bar_norm, 0);
+            tc_fence_after();
+        }
+
+        for (int j0 = 0; j0 < N; j0 += 16) {
+            float v[16];
+            tmem_ld16(tlane + (uint32_t)j0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += p.bias ? p.bias[j0 + i] : 0.f;
+            if (p.gdn) {
+                float nrm[16];
+                tmem_ld16(tlane + (uint32_t)(N + j0), nrm);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float s = sqrtf(nrm[i] + p.gdn_beta[j0 + i]);
+                    v[i] = (p.gdn == 1) ? v[i] / s : v[i] * s;
+                }
+            } else if (p.act != AIVC_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (p.act_channels == 0 || j0 + i < p.act_channels) v[i] = act_apply(p.act, v[i]);
+            }
+            if (valid) {
+                if (p.gate.data) {
+                    float g[16];
+                    load16(p.gate, gate_vec, oy, ox, j0, 16, g);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= g[i];
+                }
+                if (p.res.data) {
+                    float r[16];
+                    load16(p.res, res_vec, oy, ox, j0, 16, r);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += r[i];
+                }
+                if (p.post != AIVC_POST_NONE) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = post_apply(p.post, v[i]);
+                }
+                if (p.out_scale) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= p.out_scale[j0 + i];
+                }
+                store16(p.out, out_vec, oy, ox, j0, 16, v);
+            }
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int rowbytes) {
+    return rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : (rowbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+               const cuuint32_t *box, int rowbytes, const char *what) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) AIVC_FAIL("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, ones,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(rowbytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AIVC_FAIL("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
+void pick_tile(int mh, int mw, int *tw, int *th) {
+    int best = 1 << 30, btw = 16;
+    for (int w = 128; w >= 8; w >>= 1) {       // prefer wide tiles on ties
+        const int h = 128 / w;
+        const int tiles = ceil_div(mw, w) * ceil_div(mh, h);
+        if (tiles < best) { best = tiles; btw = w; }
+    }
+    *tw = btw;
+    *th = 128 / btw;
+}
+
+template <int BK>
+int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, const TcParams &p, dim3 grid,
+              size_t smem, cudaStream_t st) {
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+    conv_tc_kernel<BK><<<grid, NTHREADS, smem, st>>>(a, b, g, p);
+    AIVC_CHECK_LAUNCH("conv_tc_kernel");
+    return 0;
+}
+
+}  // namespace
+
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
-    (void)op; (void)st;
-    AIVC_FAIL("tcgen05 engine not built yet");
+    const int k = op->k, cin = op->in.c, cout = op->out.c;
+    if (op->in.dtype != AIVC_BF16) AIVC_FAIL("conv_tc: input feature map must be bf16");
+    if (cin % 16 || cout % 16 || cout > 256) AIVC_FAIL("conv_tc: cin %d / cout %d not tileable", cin, cout);
+    if (k * k > MAX_TAPS) AIVC_FAIL("conv_tc: kernel size %d unsupported", k);
+    if (op->in.c_off % 8 || op->in.c_stride % 8) AIVC_FAIL("conv_tc: input channel view must be 16-byte aligned");
+    const int gdn = op->act == AIVC_ACT_GDN ? 1 : (op->act == AIVC_ACT_IGDN ? 2 : 0);
+    if (gdn && !(cout == 16 || cout == 32 || cout == 64 || cout == 128))
+        AIVC_FAIL("conv_tc: fused GDN supports 16/32/64/128 channels, got %d", cout);
+    if (gdn && !op->bias) AIVC_FAIL("conv_tc: fused GDN expects a bias");
+    const int BK = (cin % 64 == 0) ? 64 : ((cin % 32 == 0) ? 32 : 16);
+    const int rowb = BK * 2;
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = to_dev(op->out);
+    if (op->residual.data) p.res = to_dev(op->residual);
+    if (op->gate.data) p.gate = to_dev(op->gate);
+    p.bias = op->bias; p.gdn_beta = op->gdn_beta; p.out_scale = op->out_scale;
+    p.cout = cout; p.kchunks = cin / BK;
+    p.act = gdn ? AIVC_ACT_NONE : op->act; p.post = op->post; p.act_channels = op->act_channels; p.gdn = gdn;
+    p.kg = cout < 64 ? cout : 64;
+    int need_cols = gdn ? 2 * cout : cout;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
+    p.a_bytes = 128u * rowb;
+    p.b_bytes = (uint32_t)cout * rowb;
+    p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+
+    const aivc_fmap &in = op->in;
+    const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
+    CUtensorMap tmA, tmB, tmG;
+    memset(&tmG, 0, sizeof(tmG));
+    int nphase = 1;
+    if (op->kind == 0) {
+        const int half = k / 2;
+        if (k > 1 && in.pad < half) AIVC_FAIL("conv_tc: input border %d < %d", in.pad, half);
+        p.mh = op->out.h; p.mw = op->out.w; p.out_step = 1;
+        pick_tile(p.mh, p.mw, &p.tw, &p.th);
+        Phase &ph = p.ph[0];
+        ph.ntaps = k * k;
+        void *base = (char *)in.data + (size_t)in.c_off * 2;
+        if (op->stride == 1) {
+            p.mode = 0;
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx) {
+                    const int t = ky * k + kx;
+                    ph.ax[t] = (signed char)(kx - half + in.pad);
+                    ph.ay[t] = (signed char)(ky - half + in.pad);
+                    ph.widx[t] = (unsigned char)t;
+                }
+            cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
+            cuuint64_t strides[2] = {pix_b, row_b};
+            cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+            if (encode_map(&tmA, base, 3, dims, strides, box, rowb, "A/3d")) return 1;
+        } else {
+            p.mode = 1;
+            if ((in.pitch & 1) || (in.rows & 1)) AIVC_FAIL("conv_tc: stride-2 input needs even pitch/rows");
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx) {
+                    const int t = ky * k + kx;
+                    const int ex = kx - half + in.pad, ey = ky - half + in.pad;
+                    ph.ax[t] = (signed char)(ex >> 1); ph.qx[t] = (unsigned char)(ex & 1);
+                    ph.ay[t] = (signed char)(ey >> 1); ph.qy[t] = (unsigned char)(ey & 1);
+                    ph.widx[t] = (unsigned char)t;
+                }
+            cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)(in.pitch / 2), 2, (cuuint64_t)(in.rows / 2)};
+            cuuint64_t strides[4] = {pix_b, 2 * pix_b, row_b, 2 * row_b};
+            cuuint32_t box[5] = {(cuuint32_t)BK, 1, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th};
+            if (encode_map(&tmA, base, 5, dims, strides, box, rowb, "A/5d")) return 1;
+        }
+    } else {
+        // transposed conv: 4 output phases, zero padding = TMA fill outside the *interior*
+        const int pad = (k + 1) / 2 - 1;
+        p.mode = 0; p.mh = in.h; p.mw = in.w; p.out_step = 2;
+        pick_tile(p.mh, p.mw, &p.tw, &p.th);
+        nphase = 4;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                Phase &ph = p.ph[py * 2 + px];
+                ph.out_py = py; ph.out_px = px;
+                int n = 0;
+                for (int ky = 0; ky < k; ++ky) {
+                    if ((py + pad - ky) & 1) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        if ((px + pad - kx) & 1) continue;
+                        ph.ay[n] = (signed char)((py + pad - ky) / 2);
+                        ph.ax[n] = (signed char)((px + pad - kx) / 2);
+                        ph.widx[n] = (unsigned char)(ky * k + kx);
+                        ++n;
+                    }
+                }
+                ph.ntaps = n;
+            }
+        void *base = (char *)in.data + ((size_t)in.pad * in.pitch + in.pad) * pix_b + (size_t)in.c_off * 2;
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
+        cuuint64_t strides[2] = {pix_b, row_b};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+        if (encode_map(&tmA, base, 3, dims, strides, box, rowb, "A/tconv")) return 1;
+    }
+    p.tiles_x = ceil_div(p.mw, p.tw);
+    const int tiles_y = ceil_div(p.mh, p.th);
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(k * k)};
+        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)cout, 1};
+        if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, rowb, "B")) return 1;
+    }
+    size_t smem = 1024 + (size_t)NSTAGES * p.stage_bytes;
+    if (gdn) {
+        cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)cout * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.kg, (cuuint32_t)cout};
+        if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, p.kg * 2, "gamma")) return 1;
+        smem += (size_t)128 * cout * 2 + (size_t)cout * cout * 2;
+    }
+    if (smem > 227 * 1024) AIVC_FAIL("conv_tc: %zu bytes of shared memory needed", smem);
+    dim3 grid(p.tiles_x * tiles_y, 1, nphase);
+    if (BK == 64) return launch_bk<64>(tmA, tmB, tmG, p, grid, smem, st);
+    if (BK == 32) return launch_bk<32>(tmA, tmB, tmG, p, grid, smem, st);
+    return launch_bk<16>(tmA, tmB, tmG, p, grid, smem, st);
 }
