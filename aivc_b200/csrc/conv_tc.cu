@@ -463,7 +463,7 @@ template <int BK>
 int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, const TcParams &p, dim3 grid,
               size_t smem, cudaStream_t st) {
     AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024));
+                                         220 * 1024));
     conv_tc_kernel<BK><<<grid, NTHREADS, smem, st>>>(a, b, g, p);
     AIVC_CHECK_LAUNCH("conv_tc_kernel");
     return 0;
@@ -587,7 +587,7 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
         if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, p.kg * 2, "gamma")) return 1;
         smem += (size_t)128 * cout * 2 + (size_t)cout * cout * 2;
     }
-    if (smem > 227 * 1024) AIVC_FAIL("conv_tc: %zu bytes of shared memory needed", smem);
+    if (smem > 220 * 1024) AIVC_FAIL("conv_tc: %zu bytes of shared memory needed", smem);
     dim3 grid(p.tiles_x * tiles_y, 1, nphase);
     if (BK == 64) return launch_bk<64>(tmA, tmB, tmG, p, grid, smem, st);
     if (BK == 32) return launch_bk<32>(tmA, tmB, tmG, p, grid, smem, st);
