@@ -38,6 +38,9 @@ _SIGS = {
     # name: (restype, argtypes)
     'aivc_abi_version': (C.c_int, []),
     'aivc_last_error': (C.c_char_p, []),
+    'aivc_launch_count': (C.c_ulonglong, []),
+    'aivc_profile_enable': (C.c_int, [C.c_int]),
+    'aivc_profile_read': (C.c_int, [C.POINTER(C.c_double)]),
     'aivc_pack_conv_weight': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 6),

@@ -7,6 +7,20 @@ int conv_simt_run(const aivc_conv_op *op, cudaStream_t st);
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
+unsigned long long g_aivc_launches = 0;
+
+// ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every conv stage
+#include <vector>
+struct StageRec { cudaEvent_t a, b; int engine; double flops; };
+static std::vector<StageRec> g_prof;
+static bool g_prof_on = false;
+
+static double stage_flops(const aivc_conv_op *op) {
+    const double px = op->kind == 0 ? (double)op->out.h * op->out.w : (double)op->in.h * op->in.w;
+    double f = 2.0 * op->k * op->k * op->in.c * op->out.c * px;
+    if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN) f += 2.0 * op->out.c * op->out.c * (double)op->out.h * op->out.w;
+    return f;
+}
 
 void aivc_set_error(const char *fmt, ...) {
     va_list ap;
@@ -58,9 +72,45 @@ const char *aivc_last_error(void) { return g_err; }
 
 int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
     if (validate_conv(op)) return 1;
-    if (op->engine == AIVC_ENGINE_SIMT) return conv_simt_run(op, (cudaStream_t)stream);
-    if (op->engine == AIVC_ENGINE_TC) return conv_tc_run(op, (cudaStream_t)stream);
-    AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
+    if (op->engine != AIVC_ENGINE_SIMT && op->engine != AIVC_ENGINE_TC) AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
+    StageRec r;
+    if (g_prof_on) {
+        AIVC_CHECK_CUDA(cudaEventCreate(&r.a));
+        AIVC_CHECK_CUDA(cudaEventCreate(&r.b));
+        r.engine = op->engine;
+        r.flops = stage_flops(op);
+        AIVC_CHECK_CUDA(cudaEventRecord(r.a, (cudaStream_t)stream));
+    }
+    const int rc = op->engine == AIVC_ENGINE_SIMT ? conv_simt_run(op, (cudaStream_t)stream)
+                                                  : conv_tc_run(op, (cudaStream_t)stream);
+    if (g_prof_on) {
+        AIVC_CHECK_CUDA(cudaEventRecord(r.b, (cudaStream_t)stream));
+        g_prof.push_back(r);
+    }
+    return rc;
+}
+
+unsigned long long aivc_launch_count(void) { return g_aivc_launches; }
+
+int aivc_profile_enable(int on) {
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+
+// out[0..5] = tc_ms, tc_flops, tc_stages, simt_ms, simt_flops, simt_stages (device must be idle or
+// the caller synchronised; this call synchronises on the last event of every stage)
+int aivc_profile_read(double *out) {
+    for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    for (auto &r : g_prof) {
+        AIVC_CHECK_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        const int o = r.engine == AIVC_ENGINE_TC ? 0 : 3;
+        out[o] += ms; out[o + 1] += r.flops; out[o + 2] += 1.0;
+    }
+    return 0;
 }
 
 int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {

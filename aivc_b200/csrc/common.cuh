@@ -19,8 +19,10 @@ void aivc_set_error(const char *fmt, ...);
         cudaError_t _e = (expr);                                                           \
         if (_e != cudaSuccess) AIVC_FAIL("%s failed: %s", #expr, cudaGetErrorString(_e));  \
     } while (0)
+extern unsigned long long g_aivc_launches;   // kernels launched by this library (this process)
 #define AIVC_CHECK_LAUNCH(name)                                                            \
     do {                                                                                   \
+        ++g_aivc_launches;                                                                 \
         cudaError_t _e = cudaGetLastError();                                               \
         if (_e != cudaSuccess) AIVC_FAIL("launch of %s failed: %s", name, cudaGetErrorString(_e)); \
     } while (0)

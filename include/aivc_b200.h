@@ -93,6 +93,13 @@ typedef struct {
 int aivc_abi_version(void);
 const char *aivc_last_error(void);
 
+/* ---- instrumentation (bench.py): kernels launched so far by this process, and optional
+ * CUDA-event timing of every convolution stage, summed per engine.
+ * aivc_profile_read: out[0..5] = tc_ms, tc_flops, tc_stages, simt_ms, simt_flops, simt_stages */
+unsigned long long aivc_launch_count(void);
+int aivc_profile_enable(int on);
+int aivc_profile_read(double *out);
+
 /* ---- convolution stack ------------------------------------------------------------- */
 /* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or
  * ConvTranspose2d [cin][cout][k][k] fp32 (device).  dst: SIMT [k*k][cin][cout] fp32,
