@@ -42,16 +42,17 @@ _SIGS = {
     'aivc_profile_enable': (C.c_int, [C.c_int]),
     'aivc_profile_read': (C.c_int, [C.POINTER(C.c_double)]),
     'aivc_pack_conv_weight': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 6),
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 4),
     'aivc_conv2d_fused': (C.c_int, [C.POINTER(ConvOp), C.c_void_p]),
     'aivc_conv2d_fused_seq': (C.c_int, [C.POINTER(ConvOp), C.c_int, C.c_void_p]),
     'aivc_nchw_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
     'aivc_fmap_to_nchw': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
     'aivc_fill_border': (C.c_int, [C.POINTER(FMap), C.c_void_p]),
-    'aivc_yuv420_to_fmap': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(FMap),
-                                      C.c_void_p]),
-    'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int] + [C.POINTER(FMap)] * 2 + [C.c_void_p]),
+    'aivc_yuv420_to_fmap': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(FMap), C.c_void_p]),
+    'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int, C.c_int] + [C.POINTER(FMap)] * 2
+                        + [C.c_void_p]),
     'aivc_warp_blend_nchw': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
     'aivc_finalize_frame': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.POINTER(FMap), C.c_void_p]),

@@ -14,12 +14,15 @@ It follows real_life/decode.py:455-898 (decoder) and its mirror for the encoder
 int16 symbols + 16-bit CDF bounds (encoder) or fp32 Laplace scales (decoder).
 """
 import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+from types import SimpleNamespace
 
 import numpy as np
 import torch
 
 from . import _lib, entropy
-from ._lib import F32
+from ._lib import F32, BF16
 from .gop import FRAME_I, FRAME_P, FRAME_B, coding_order
 from .plan import Plan, Buffer, Config
 
@@ -49,25 +52,28 @@ def _gain_vec(gm, idx_rate, mode):
 class CondNetEngine:
     """Kernel plans and staging buffers of one ConditionalNet at a fixed frame size."""
 
-    def __init__(self, net, h, w, in_buf, ref_off, ref_c, device, cfg, idx_rate=0.):
+    def __init__(self, net, h, w, in_buf, in_c, ref_off, ref_c, device, cfg, idx_rate=0., levels=False):
         self.net, self.device = net, device
         cy, cz, csc = net.nb_ft_y, net.nb_ft_z, net.out_c_shortcut_y
         self.cy, self.cz, self.csc = cy, cz, csc
         (hy, wy), (hz, wz) = latent_dims(h, w)
         self.dims_y, self.dims_z = (hy, wy), (hz, wz)
         exact = Config(precision='fp32')           # hyperprior: exact engine (sigma steers the coder)
-        self.g_s = Plan(net.g_s, hy, wy, cy + csc, device, cfg)
+        tc = cfg.precision == 'bf16'
+        embed = (lambda off: (in_buf.c, off, (1.0 / 255.0) if levels else 1.0)) if tc else (lambda off: None)
+        self.g_s = Plan(net.g_s, hy, wy, cy + csc, device, cfg, pad_cout=16 if tc else 0)
         self.gs_in = self.g_s.src.buf
         self.has_ref = getattr(net, 'g_a_ref', None) is not None
         self.h_s = Plan(net.h_s, hz, wz, cz, device, exact)
         if getattr(net, 'g_a', None) is not None:        # a decoder-only model has no analysis side
-            self.g_a = Plan(net.g_a, h, w, in_buf.c, device, cfg, src_buf=in_buf,
-                            out_scale=torch.ones(cy))
+            self.g_a = Plan(net.g_a, h, w, in_c, device, cfg, src_buf=in_buf,
+                            out_scale=torch.ones(cy), in_embed=embed(0))
             self.h_a = Plan(net.h_a, hy, wy, cy, device, exact, src_buf=self.g_a.dst.buf,
                             dst_into=(self.h_s.src.buf, 0), out_post='round_clamp')
         if self.has_ref:
             self.g_a_ref = Plan(net.g_a_ref, h, w, ref_c, device, cfg, src_buf=in_buf,
-                                src_c_off=ref_off, dst_into=(self.gs_in, cy))
+                                src_c_off=0 if tc else ref_off, dst_into=(self.gs_in, cy),
+                                in_embed=embed(ref_off))
         self.table = entropy.z_table_u16(net.pdf_z)
         self.gains = {}
         for ft in (FRAME_I, FRAME_P, FRAME_B):
@@ -75,19 +81,27 @@ class CondNetEngine:
             self.gains[ft] = (_gain_vec(gm, idx_rate, 'enc').float().to(device).contiguous(),
                               _gain_vec(gm, idx_rate, 'dec').float().to(device).contiguous())
         n_y, n_z = cy * hy * wy, cz * hz * wz
+        self.n_y, self.n_z = n_y, n_z
         dev = dict(device=device)
         self.q_dev = torch.empty(n_y, dtype=torch.int16, **dev)
         self.bounds_dev = torch.empty(n_y, dtype=torch.int32, **dev)
         self.nz_dev = torch.zeros(cy, dtype=torch.int32, **dev)
         self.z_dev = torch.empty(n_z, dtype=torch.int16, **dev)
         self.b_dev = torch.empty(n_y, dtype=torch.float32, **dev)
-        pin = dict(pin_memory=True)
-        self.q_host = torch.empty(n_y, dtype=torch.int16, **pin)
-        self.bounds_host = torch.empty(n_y, dtype=torch.int32, **pin)
-        self.nz_host = torch.empty(cy, dtype=torch.int32, **pin)
-        self.z_host = torch.empty(n_z, dtype=torch.int16, **pin)
-        self.b_host = torch.empty(n_y, dtype=torch.float32, **pin)
-        self.last = {}
+        self._slots = []
+
+    # -- host staging: one pinned slot per latent in flight, so the GPU never waits for the coder
+    def slot(self, i):
+        while len(self._slots) <= i:
+            pin = dict(pin_memory=True)
+            self._slots.append(SimpleNamespace(
+                z=torch.empty(self.n_z, dtype=torch.int16, **pin),
+                bounds=torch.empty(self.n_y, dtype=torch.int32, **pin),
+                nz=torch.empty(self.cy, dtype=torch.int32, **pin),
+                b=torch.empty(self.n_y, dtype=torch.float32, **pin),
+                q=torch.empty(self.n_y, dtype=torch.int16, **pin),
+                event=torch.cuda.Event(), sec_y=None, first_of_i_frame=False))
+        return self._slots[i]
 
     def _yhat_view(self):
         return self.gs_in.view(0, self.cy)
@@ -99,9 +113,10 @@ class CondNetEngine:
             full = self.gs_in.t.view(self.gs_in.rows, self.gs_in.pitch, self.gs_in.c)
             full[:, :, self.cy:].zero_()
 
-    def encode(self, frame_type, use_shortcut, first_of_i_frame=False):
-        """Runs analysis + synthesis; returns the two bitstream sections. The synthesis
-        output stays in ``self.g_s.dst``."""
+    # ---------------------------------------------------------------- encoder
+    def encode_launch(self, sl, frame_type, use_shortcut, first_of_i_frame=False):
+        """Enqueue analysis, quantisation and synthesis; symbols / CDF bounds are copied to the
+        pinned slot `sl` asynchronously.  No host synchronisation."""
         L, st = _lib.lib(), _lib.stream_ptr()
         enc_gain, dec_gain = self.gains[frame_type]
         self.g_a.ops[len(self.g_a.ops) - 1].out_scale = enc_gain.data_ptr()
@@ -109,51 +124,89 @@ class CondNetEngine:
         self.h_a.run()
         zf = self.h_s.in_fmap
         _lib.check(L.aivc_fmap_to_i16(C.byref(zf), self.z_dev.data_ptr(), st))
-        self.z_host.copy_(self.z_dev, non_blocking=True)
+        sl.z.copy_(self.z_dev, non_blocking=True)
         self.h_s.run()
         self.nz_dev.zero_()
         yf, hsf, yh = self.g_a.out_fmap, self.h_s.out_fmap, self._yhat_view()
         _lib.check(L.aivc_quantize_latent(C.byref(yf), C.byref(hsf), dec_gain.data_ptr(),
                                           self.q_dev.data_ptr(), self.bounds_dev.data_ptr(),
                                           self.nz_dev.data_ptr(), C.byref(yh), st))
-        self.bounds_host.copy_(self.bounds_dev, non_blocking=True)
-        self.nz_host.copy_(self.nz_dev, non_blocking=True)
+        sl.bounds.copy_(self.bounds_dev, non_blocking=True)
+        sl.nz.copy_(self.nz_dev, non_blocking=True)
+        sl.event.record()
+        sl.first_of_i_frame = first_of_i_frame
         self._shortcut(use_shortcut)
         self.g_s.run()
-        torch.cuda.current_stream().synchronize()
+
+    def encode_finish(self, sl):
+        """Host side (any thread): range-code the latent of slot `sl` -> two bitstream sections."""
+        sl.event.synchronize()
         (hy, wy), (hz, wz) = self.dims_y, self.dims_z
-        sec_z = entropy.encode_z(self.table, self.z_host.numpy().reshape(self.cz, hz, wz))
-        sec_y = entropy.encode_y(self.bounds_host.numpy().view(np.uint32).reshape(self.cy, hy * wy),
-                                 self.nz_host.numpy())
-        if first_of_i_frame:    # bitstream.py:292-296
+        sec_z = entropy.encode_z(self.table, sl.z.numpy().reshape(self.cz, hz, wz))
+        sec_y = entropy.encode_y(sl.bounds.numpy().view(np.uint32).reshape(self.cy, hy * wy),
+                                 sl.nz.numpy())
+        if sl.first_of_i_frame:    # bitstream.py:292-296
             sec_z = (0).to_bytes(4, 'big') * 2 + sec_z
         return sec_z + sec_y
 
-    def decode(self, sec_z, sec_y, frame_type, use_shortcut):
+    def encode(self, frame_type, use_shortcut, first_of_i_frame=False):
+        sl = self.slot(0)
+        self.encode_launch(sl, frame_type, use_shortcut, first_of_i_frame)
+        return self.encode_finish(sl)
+
+    # ---------------------------------------------------------------- decoder
+    def entropy_launch(self, sl, sec_z, sec_y):
+        """z: host range decode -> device -> h_s -> Laplace scales back to the pinned slot."""
         L, st = _lib.lib(), _lib.stream_ptr()
-        _, dec_gain = self.gains[frame_type]
         (hy, wy), (hz, wz) = self.dims_y, self.dims_z
         z = entropy.decode_z(self.table, sec_z, self.cz, hz, wz)
-        self.z_host.copy_(torch.from_numpy(z).reshape(-1))
-        self.z_dev.copy_(self.z_host, non_blocking=True)
+        sl.z.copy_(torch.from_numpy(z).reshape(-1))
+        sl.sec_y = sec_y
+        self._hyper_from_slot(sl)
+        hs_y = self._hs_view()
+        _lib.check(L.aivc_laplace_scale(C.byref(hs_y), self.cy, self.b_dev.data_ptr(), st))
+        sl.b.copy_(self.b_dev, non_blocking=True)
+        sl.event.record()
+
+    def _hs_view(self):
+        hs_y = _lib.FMap.from_buffer_copy(self.h_s.out_fmap)
+        hs_y.h, hs_y.w = self.dims_y                  # h_s(z)[:, :, :h_y, :w_y]  decode.py:853
+        return hs_y
+
+    def _hyper_from_slot(self, sl):
+        L, st = _lib.lib(), _lib.stream_ptr()
+        self.z_dev.copy_(sl.z, non_blocking=True)
         zf = self.h_s.in_fmap
         _lib.check(L.aivc_i16_to_fmap(self.z_dev.data_ptr(), C.byref(zf), st))
         self.h_s.run()
-        hsf = self.h_s.out_fmap
-        hs_y = _lib.FMap.from_buffer_copy(hsf)
-        hs_y.h, hs_y.w = hy, wy                       # h_s(z)[:, :, :h_y, :w_y]  decode.py:853
-        _lib.check(L.aivc_laplace_scale(C.byref(hs_y), self.cy, self.b_dev.data_ptr(), st))
-        self.b_host.copy_(self.b_dev, non_blocking=True)
-        self._shortcut(use_shortcut)                  # overlaps the host range decoder
-        torch.cuda.current_stream().synchronize()
-        q = entropy.decode_y(sec_y, self.b_host.numpy().reshape(self.cy, hy, wy), self.cy, hy, wy)
-        self.q_host.copy_(torch.from_numpy(q).reshape(-1))
-        self.q_dev.copy_(self.q_host, non_blocking=True)
-        yh = self._yhat_view()
+
+    def entropy_finish(self, sl):
+        """Host side (any thread): range-decode y of slot `sl` into its pinned q buffer."""
+        sl.event.synchronize()
+        (hy, wy) = self.dims_y
+        q = entropy.decode_y(sl.sec_y, sl.b.numpy().reshape(self.cy, hy, wy), self.cy, hy, wy)
+        sl.q.copy_(torch.from_numpy(q).reshape(-1))
+        return True
+
+    def synth_launch(self, sl, frame_type, use_shortcut, rerun_hyper=True):
+        """y^ = (q + mu) * gain, shortcut, g_s.  `rerun_hyper`: recompute h_s(z) of this slot
+        (another latent may have used the hyper-decoder buffers since entropy_launch)."""
+        L, st = _lib.lib(), _lib.stream_ptr()
+        _, dec_gain = self.gains[frame_type]
+        if rerun_hyper:
+            self._hyper_from_slot(sl)
+        self.q_dev.copy_(sl.q, non_blocking=True)
+        hs_y, yh = self._hs_view(), self._yhat_view()
         _lib.check(L.aivc_dequantize_latent(self.q_dev.data_ptr(), C.byref(hs_y), dec_gain.data_ptr(),
                                             C.byref(yh), st))
+        self._shortcut(use_shortcut)
         self.g_s.run()
-        self.last = {'z': z, 'q': q}
+
+    def decode(self, sec_z, sec_y, frame_type, use_shortcut):
+        sl = self.slot(0)
+        self.entropy_launch(sl, sec_z, sec_y)
+        self.entropy_finish(sl)
+        self.synth_launch(sl, frame_type, use_shortcut, rerun_hyper=False)
 
 
 class FrameCodec:
@@ -164,14 +217,22 @@ class FrameCodec:
         self.device = torch.device(device)
         self.cfg = cfg or Config()
         self.idx_rate = idx_rate
+        # bf16 engine: pixel inputs live in 16-channel bf16 pixels (zero padded) holding 8-bit LEVEL
+        # units -- exact in bf16 -- with a 2-pixel replicate border for the 5x5 first conv; the
+        # 1/255 is folded into the first-layer weights.  fp32 engine: plain [0,1] fp32 pixels.
+        self.levels = self.cfg.precision == 'bf16'
         with torch.cuda.device(self.device):
-            self.mof_in = Buffer(h, w, 9, 0, F32, self.device)
-            self.codec_in = Buffer(h, w, 6, 0, F32, self.device)
+            if self.levels:
+                self.mof_in = Buffer(h, w, 16, 2, BF16, self.device)
+                self.codec_in = Buffer(h, w, 16, 2, BF16, self.device)
+            else:
+                self.mof_in = Buffer(h, w, 9, 0, F32, self.device)
+                self.codec_in = Buffer(h, w, 6, 0, F32, self.device)
             self.skip = Buffer(h, w, 3, 0, F32, self.device)
-            self.mof = CondNetEngine(model.mode_net.mode_net, h, w, self.mof_in, 3, 6, self.device,
-                                     self.cfg, idx_rate)
-            self.codec = CondNetEngine(model.codec_net.codec_net, h, w, self.codec_in, 3, 3,
-                                       self.device, self.cfg, idx_rate)
+            self.mof = CondNetEngine(model.mode_net.mode_net, h, w, self.mof_in, 9, 3, 6, self.device,
+                                     self.cfg, idx_rate, self.levels)
+            self.codec = CondNetEngine(model.codec_net.codec_net, h, w, self.codec_in, 6, 3, 3,
+                                       self.device, self.cfg, idx_rate, self.levels)
             hc, wc = (h + 1) // 2, (w + 1) // 2
             self.zero_planes = (torch.zeros(h * w, dtype=torch.uint8, device=self.device),
                                 torch.zeros(hc * wc, dtype=torch.uint8, device=self.device),
@@ -188,11 +249,12 @@ class FrameCodec:
         u8 = 1 if y.dtype == torch.uint8 else 0
         fm = buf.view(c_off, 3)
         _lib.check(_lib.lib().aivc_yuv420_to_fmap(y.data_ptr(), u.data_ptr(), v.data_ptr(), u8,
-                                                  C.byref(fm), _lib.stream_ptr()))
+                                                  1 if self.levels else 0, C.byref(fm),
+                                                  _lib.stream_ptr()))
 
     def _zero_pred(self):
         full = self.codec_in.t.view(self.codec_in.rows, self.codec_in.pitch, self.codec_in.c)
-        full[:, :, 3:].zero_()
+        full[:, :, 3:6].zero_()
 
     def _motion(self, frame_type):
         L = _lib.lib()
@@ -200,8 +262,8 @@ class FrameCodec:
         prev, nxt = self.mof_in.view(3, 3), self.mof_in.view(6, 3)
         pred, skip = self.codec_in.view(3, 3), self.skip.view(0, 3)
         _lib.check(L.aivc_warp_blend(C.byref(mo), C.byref(prev), C.byref(nxt),
-                                     1 if frame_type == FRAME_P else 0, C.byref(pred), C.byref(skip),
-                                     _lib.stream_ptr()))
+                                     1 if frame_type == FRAME_P else 0, 1 if self.levels else 0,
+                                     C.byref(pred), C.byref(skip), _lib.stream_ptr()))
 
     def _finalize(self, frame_type, out_planes):
         cod = _lib.FMap.from_buffer_copy(self.codec.g_s.out_fmap)
@@ -252,21 +314,74 @@ class FrameCodec:
         return rec
 
     def encode_gop(self, frames, gop):
-        """frames: {'frame_i': (y,u,v) device planes}. Returns ({name: bytes}, {name: planes})."""
-        out_b, rec = {}, {}
-        for f in coding_order(gop):
-            e = gop[f]
-            out_b[f], rec[f] = self.encode_frame(frames[f], e['type'], rec.get(e['prev_ref']),
-                                                 rec.get(e['next_ref']))
+        """frames: {'frame_i': (y,u,v) device planes}. Returns ({name: bytes}, {name: planes}).
+        The GPU runs ahead through the whole GOP; the serial range coder of every latent runs on
+        host worker threads as soon as its symbols have landed in pinned memory."""
+        pool = self._pool()
+        rec, futs = {}, {}
+        with torch.cuda.device(self.device):
+            for i, f in enumerate(coding_order(gop)):
+                e = gop[f]
+                ft = e['type']
+                self._pack(frames[f], self.codec_in, 0)
+                parts = []
+                if ft == FRAME_I:
+                    self._zero_pred()
+                else:
+                    self._pack(frames[f], self.mof_in, 0)
+                    self._refs(ft, rec.get(e['prev_ref']), rec.get(e['next_ref']))
+                    sl = self.mof.slot(i)
+                    self.mof.encode_launch(sl, ft, ft == FRAME_B)
+                    parts.append(pool.submit(self.mof.encode_finish, sl))
+                    self._motion(ft)
+                sl = self.codec.slot(i)
+                self.codec.encode_launch(sl, ft, ft != FRAME_I, first_of_i_frame=(ft == FRAME_I))
+                parts.append(pool.submit(self.codec.encode_finish, sl))
+                rec[f] = self.new_planes()
+                self._finalize(ft, rec[f])
+                futs[f] = parts
+        out_b = {f: b''.join(p.result() for p in parts) for f, parts in futs.items()}
         return out_b, rec
 
     def decode_gop(self, frame_bytes, gop):
-        rec = {}
-        for f in coding_order(gop):
-            e = gop[f]
-            rec[f] = self.decode_frame(frame_bytes[f], e['type'], rec.get(e['prev_ref']),
-                                       rec.get(e['next_ref']))
+        """Two passes.  (1) entropy: every latent's z is decoded, its hyper-decoder run, and its
+        y stream handed to a host worker -- none of this depends on reconstructed pixels.
+        (2) reconstruction in coding order, consuming the symbols as the workers deliver them."""
+        pool = self._pool()
+        order = coding_order(gop)
+        futs = {}
+        with torch.cuda.device(self.device):
+            for i, f in enumerate(order):
+                secs = entropy.split_sections(frame_bytes[f])
+                ft = gop[f]['type']
+                if ft != FRAME_I:
+                    sl = self.mof.slot(i)
+                    self.mof.entropy_launch(sl, secs[0], secs[1])
+                    futs[(f, 0)] = pool.submit(self.mof.entropy_finish, sl)
+                sl = self.codec.slot(i)
+                self.codec.entropy_launch(sl, secs[2], secs[3])
+                futs[(f, 1)] = pool.submit(self.codec.entropy_finish, sl)
+            rec = {}
+            for i, f in enumerate(order):
+                e = gop[f]
+                ft = e['type']
+                if ft == FRAME_I:
+                    self._zero_pred()
+                else:
+                    self._refs(ft, rec.get(e['prev_ref']), rec.get(e['next_ref']))
+                    futs[(f, 0)].result()
+                    self.mof.synth_launch(self.mof.slot(i), ft, ft == FRAME_B)
+                    self._motion(ft)
+                futs[(f, 1)].result()
+                self.codec.synth_launch(self.codec.slot(i), ft, ft != FRAME_I)
+                rec[f] = self.new_planes()
+                self._finalize(ft, rec[f])
         return rec
+
+    def _pool(self):
+        if getattr(self, '_tp', None) is None:
+            self._tp = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 4))))
+        return self._tp
 
 
 def planes_to_device(yuv_u8, device):

@@ -68,7 +68,7 @@ __global__ void i16_to_fmap_kernel(const int16_t *__restrict__ src, FMap dst) {
 // ---------------------------------------------------------------- InputLayer
 template <bool U8>
 __global__ void yuv420_to_fmap_kernel(const void *__restrict__ yp, const void *__restrict__ up,
-                                      const void *__restrict__ vp, FMap dst) {
+                                      const void *__restrict__ vp, FMap dst, float scale) {
     const int wc = (dst.w + 1) / 2;
     const size_t n = (size_t)dst.h * dst.w;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -77,13 +77,15 @@ __global__ void yuv420_to_fmap_kernel(const void *__restrict__ yp, const void *_
         const size_t ci = (size_t)(y / 2) * wc + (x / 2);
         float a, b, c;
         if (U8) {
-            a = (float)((const uint8_t *)yp)[i] / 255.f;
-            b = (float)((const uint8_t *)up)[ci] / 255.f;
-            c = (float)((const uint8_t *)vp)[ci] / 255.f;
+            a = (float)((const uint8_t *)yp)[i];
+            b = (float)((const uint8_t *)up)[ci];
+            c = (float)((const uint8_t *)vp)[ci];
+            if (scale != 1.f) { a /= 255.f; b /= 255.f; c /= 255.f; }   // [0,1] units, like x/255 in torch
         } else {
             a = ((const float *)yp)[i];
             b = ((const float *)up)[ci];
             c = ((const float *)vp)[ci];
+            if (scale == 1.f) { a *= 255.f; b *= 255.f; c *= 255.f; }   // level units
         }
         fm_store(dst, y, x, 0, a);
         fm_store(dst, y, x, 1, b);
@@ -129,7 +131,7 @@ __device__ __forceinline__ float bilerp_sample(const Bilerp &b, int w, int h, L 
 }
 
 __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p, FMap pred,
-                                  FMap skip) {
+                                  FMap skip, int levels) {
     const int h = pred.h, w = pred.w;
     const size_t n = (size_t)h * w;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -148,8 +150,10 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
         for (int ch = 0; ch < 3; ++ch) {
             const float a = bilerp_sample(bp, w, h, [&](int yy, int xx) { return fm_load(prev, yy, xx, ch); });
             const float b = bilerp_sample(bn, w, h, [&](int yy, int xx) { return fm_load(next, yy, xx, ch); });
-            const float xw = beta * a + (1.f - beta) * b;
+            float xw = beta * a + (1.f - beta) * b;
+            // level-unit refs/pred (bf16 engine: 8-bit levels are exact in bf16); skip is in [0,1]
             fm_store(pred, y, x, ch, xw * alpha);             // warped_ref * alpha  (decode.py:542)
+            if (levels) xw /= 255.f;
             fm_store(skip, y, x, ch, (1.f - alpha) * xw);     // (1 - alpha) * warped (decode.py:536)
         }
     }
@@ -296,25 +300,27 @@ __global__ void dequantize_latent_kernel(const int16_t *__restrict__ q, FMap hs,
 
 // ---------------------------------------------------------------- weight re-layout
 __global__ void pack_weight_kernel(const float *__restrict__ src, void *__restrict__ dst, int kind,
-                                   int k, int cin, int cout, int engine, int cin_pad, int cout_pad) {
+                                   int k, int cin, int cout, int engine, int cin_pad, int cout_pad,
+                                   int cin_off, float scale) {
     const int taps = k * k;
-    const size_t n = (engine == AIVC_ENGINE_SIMT) ? (size_t)taps * cin * cout
-                                                  : (size_t)taps * cout_pad * cin_pad;
+    const size_t n = (size_t)taps * cout_pad * cin_pad;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         int t, ci, co;
-        if (engine == AIVC_ENGINE_SIMT) {          // [tap][cin][cout]
-            co = (int)(i % cout); ci = (int)((i / cout) % cin); t = (int)(i / ((size_t)cout * cin));
+        if (engine == AIVC_ENGINE_SIMT) {          // [tap][cin_pad][cout_pad]
+            co = (int)(i % cout_pad); ci = (int)((i / cout_pad) % cin_pad);
+            t = (int)(i / ((size_t)cout_pad * cin_pad));
         } else {                                   // [tap][cout_pad][cin_pad]
             ci = (int)(i % cin_pad); co = (int)((i / cin_pad) % cout_pad);
             t = (int)(i / ((size_t)cin_pad * cout_pad));
         }
+        ci -= cin_off;                             // buffer channel -> weight channel
         float v = 0.f;
-        if (ci < cin && co < cout) {
+        if (ci >= 0 && ci < cin && co < cout) {
             // Conv2d weight [cout][cin][k][k]; ConvTranspose2d weight [cin][cout][k][k]
             const size_t s = (kind == 0) ? (((size_t)co * cin + ci) * taps + t)
                                          : (((size_t)ci * cout + co) * taps + t);
-            v = src[s];
+            v = src[s] * scale;
         }
         if (engine == AIVC_ENGINE_SIMT) ((float *)dst)[i] = v;
         else ((__nv_bfloat16 *)dst)[i] = __float2bfloat16_rn(v);
@@ -371,19 +377,21 @@ int aivc_i16_to_fmap(const int16_t *src, const aivc_fmap *dst, void *stream) {
     return 0;
 }
 
-int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, const aivc_fmap *dst,
-                        void *stream) {
+int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, int levels,
+                        const aivc_fmap *dst, void *stream) {
     if (validate_fmap(dst, "yuv420_to_fmap dst")) return 1;
     if (dst->c != 3) AIVC_FAIL("yuv420_to_fmap: destination view must have 3 channels, got %d", dst->c);
     const int g = grid_for((size_t)dst->h * dst->w);
-    if (u8) yuv420_to_fmap_kernel<true><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst));
-    else yuv420_to_fmap_kernel<false><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst));
+    const float scale = levels ? 1.f : 1.f / 255.f;
+    if (u8) yuv420_to_fmap_kernel<true><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst), scale);
+    else yuv420_to_fmap_kernel<false><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst), scale);
     AIVC_CHECK_LAUNCH("yuv420_to_fmap");
     return 0;
 }
 
 int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
-                    int frame_is_p, const aivc_fmap *pred, const aivc_fmap *skip, void *stream) {
+                    int frame_is_p, int levels, const aivc_fmap *pred, const aivc_fmap *skip,
+                    void *stream) {
     if (validate_fmap(mof, "warp mof") || validate_fmap(prev, "warp prev") ||
         validate_fmap(next, "warp next") || validate_fmap(pred, "warp pred") ||
         validate_fmap(skip, "warp skip"))
@@ -393,7 +401,7 @@ int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap
     if (prev->h != pred->h || prev->w != pred->w || next->h != pred->h || next->w != pred->w)
         AIVC_FAIL("warp_blend: reference / prediction size mismatch");
     warp_blend_kernel<<<grid_for((size_t)pred->h * pred->w), PT, 0, (cudaStream_t)stream>>>(
-        to_dev(*mof), to_dev(*prev), to_dev(*next), frame_is_p, to_dev(*pred), to_dev(*skip));
+        to_dev(*mof), to_dev(*prev), to_dev(*next), frame_is_p, to_dev(*pred), to_dev(*skip), levels);
     AIVC_CHECK_LAUNCH("warp_blend");
     return 0;
 }
@@ -473,19 +481,18 @@ int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *d
     return 0;
 }
 
-size_t aivc_packed_weight_bytes(int k, int cin, int cout, int engine, int cin_pad, int cout_pad) {
-    if (engine == AIVC_ENGINE_SIMT) return (size_t)k * k * cin * cout * sizeof(float);
-    return (size_t)k * k * cin_pad * cout_pad * 2;
+size_t aivc_packed_weight_bytes(int k, int engine, int cin_pad, int cout_pad) {
+    return (size_t)k * k * cin_pad * cout_pad * (engine == AIVC_ENGINE_SIMT ? sizeof(float) : 2);
 }
 
 int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin, int cout, int engine,
-                          int cin_pad, int cout_pad, void *stream) {
-    if (engine != AIVC_ENGINE_SIMT && (cin_pad < cin || cout_pad < cout))
+                          int cin_pad, int cout_pad, int cin_off, float scale, void *stream) {
+    if (cin_off < 0 || cin_pad < cin + cin_off || cout_pad < cout)
         AIVC_FAIL("pack_conv_weight: padded sizes smaller than logical sizes");
-    const size_t n = aivc_packed_weight_bytes(k, cin, cout, engine, cin_pad, cout_pad) /
-                     (engine == AIVC_ENGINE_SIMT ? 4 : 2);
+    const size_t n = (size_t)k * k * cin_pad * cout_pad;
     pack_weight_kernel<<<grid_for(n), PT, 0, (cudaStream_t)stream>>>(src, dst, kind, k, cin, cout,
-                                                                     engine, cin_pad, cout_pad);
+                                                                     engine, cin_pad, cout_pad, cin_off,
+                                                                     scale);
     AIVC_CHECK_LAUNCH("pack_weight");
     return 0;
 }

@@ -1,0 +1,208 @@
+// Shared device helpers of the tcgen05 engines: PTX wrappers (mbarrier, TMA, tcgen05.mma /
+// commit / ld, TMEM fences), UMMA descriptors, and the vectorised epilogue load/store.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace tcgen {
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    const uint32_t addr = smem_u32(b);
+    const long long t0 = clock64();
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();   // never hang the GPU
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand descriptor: `rowbytes` = bytes of one row (= swizzle span: 128 / 64 / 32)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int rowbytes) {
+    const uint64_t layout = rowbytes == 128 ? 2ull : (rowbytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (uint64_t)(8 * rowbytes) >> 4;       // 8-row core-matrix group stride
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    // c = f32 (1<<4), a = b = bf16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ epilogue IO
+struct VecInfo {
+    bool vec;       // 16-channel groups are 16-byte aligned
+};
+__device__ __forceinline__ bool fmap_vec_ok(const FMap &m) {
+    const int al = (m.dtype == AIVC_F32) ? 4 : 8;
+    return (m.c_off % al == 0) && (m.c_stride % al == 0) && (((uintptr_t)m.data & 15) == 0);
+}
+
+__device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, int ch0, int nvalid, float *v) {
+    const size_t base = fm_index(m, y, x, ch0);
+    if (vec && nvalid == 16) {
+        if (m.dtype == AIVC_F32) {
+            const float4 *p = reinterpret_cast<const float4 *>((const float *)m.data + base);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 t = p[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+        } else {
+            const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + base);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint4 t = p[i];
+                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[8 * i + 2 * j] = __uint_as_float(w[j] << 16);
+                    v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+                }
+            }
+        }
+    } else {
+        for (int i = 0; i < 16; ++i) v[i] = (i < nvalid) ? fm_load(m, y, x, ch0 + i) : 0.f;
+    }
+}
+
+__device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, int ch0, int nvalid,
+                                        const float *v) {
+    const int p = m.pad;
+    const int y0 = (y == 0) ? 0 : y + p, y1 = (y == m.h - 1) ? y + 2 * p : y + p;
+    const int x0 = (x == 0) ? 0 : x + p, x1 = (x == m.w - 1) ? x + 2 * p : x + p;
+    if (vec && nvalid == 16) {
+        if (m.dtype == AIVC_F32) {
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    float4 *q = reinterpret_cast<float4 *>(
+                        (float *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+        } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+            }
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    uint4 *q = reinterpret_cast<uint4 *>(
+                        (__nv_bfloat16 *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
+                    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+        }
+    } else {
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx)
+                for (int i = 0; i < nvalid; ++i) fm_store_raw(m, yy, xx, ch0 + i, v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for(int rowbytes) {
+    return rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : (rowbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+inline int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+               const cuuint32_t *box, int rowbytes, const char *what) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) AIVC_FAIL("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, ones,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(rowbytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) AIVC_FAIL("cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
+
+}  // namespace tcgen

@@ -48,7 +48,7 @@ def yuv420_to_444(y, u, v):
         nhwc = torch.empty((h, w, 3), device=y.device, dtype=torch.float32)
         fm = nchw_fmap(nhwc)
         _lib.check(L.aivc_yuv420_to_fmap(y.contiguous().float().data_ptr(), u.contiguous().float().data_ptr(),
-                                         v.contiguous().float().data_ptr(), 0, C.byref(fm), st))
+                                         v.contiguous().float().data_ptr(), 0, 0, C.byref(fm), st))
         out = torch.empty((1, 3, h, w), device=y.device, dtype=torch.float32)
         _lib.check(L.aivc_fmap_to_nchw(C.byref(fm), out.data_ptr(), st))
     return out

@@ -97,7 +97,8 @@ class Stage:
     gate: Optional[T] = None
     out_scale: Optional[torch.Tensor] = None
     engine: int = ENGINE_SIMT
-    keep: list = field(default_factory=list)   # device tensors referenced by the op
+    cin_off: int = 0                # weight input channel 0 sits at this channel of the source pixel
+    w_scale: float = 1.0            # folded into the packed weights (1/255 for level-unit inputs)
 
 
 class Graph:
@@ -222,7 +223,13 @@ class Plan:
     (Buffer, c_off) the last stage writes into (concat for free)."""
 
     def __init__(self, module, h, w, cin, device, cfg=DEFAULT, src_buf=None, src_c_off=0,
-                 dst_into=None, out_scale=None, out_post='none', in_dtype=None):
+                 dst_into=None, out_scale=None, out_post='none', in_dtype=None, in_embed=None,
+                 pad_cout=0):
+        """in_embed=(buffer_channels, offset, weight_scale): the module's `cin` input channels
+        are channels [offset, offset+cin) of a wider (zero-padded) pixel of `buffer_channels`
+        channels; the first stage's weights are embedded accordingly and scaled.
+        pad_cout: round the last stage's output channels up to this multiple (extra channels
+        get zero weights), so narrow pixel-domain outputs still fill a tensor-core tile."""
         self.cfg, self.device = cfg, torch.device(device)
         g = Graph()
         self.src = T(h, w, cin, external=True)
@@ -230,7 +237,17 @@ class Plan:
         self.stages = g.stages
         if not self.stages:
             raise ValueError('nothing to run')
+        if in_embed is not None:
+            buf_c, off, wsc = in_embed
+            for s in self.stages:
+                if s.src is self.src:
+                    s.cin_off, s.w_scale = off, wsc
+            self.src.c = buf_c
         last = self.stages[-1]
+        self.out_c = self.dst.c
+        if pad_cout and self.dst.c % pad_cout:
+            assert last.gdn is None and last.res is None and last.gate is None
+            self.dst.c = -(-self.dst.c // pad_cout) * pad_cout
         if out_scale is not None:
             last.out_scale = out_scale.detach().float().reshape(-1)
         if out_post != 'none':
@@ -306,15 +323,16 @@ class Plan:
             op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
             op.inp, op.out = s.src.fmap(), s.dst.fmap()
             wsrc = s.weight.to(dev, torch.float32).contiguous()
-            cin_pad, cout_pad = cin, cout
-            nbytes = L.aivc_packed_weight_bytes(s.k, cin, cout, s.engine, cin_pad, cout_pad)
+            w_cout, w_cin = (wsrc.shape[0], wsrc.shape[1]) if s.kind == 0 else (wsrc.shape[1], wsrc.shape[0])
+            nbytes = L.aivc_packed_weight_bytes(s.k, s.engine, cin, cout)
             wdst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.aivc_pack_conv_weight(wsrc.data_ptr(), wdst.data_ptr(), s.kind, s.k, cin, cout,
-                                               s.engine, cin_pad, cout_pad, st))
+            _lib.check(L.aivc_pack_conv_weight(wsrc.data_ptr(), wdst.data_ptr(), s.kind, s.k, w_cin, w_cout,
+                                               s.engine, cin, cout, s.cin_off, s.w_scale, st))
             op.weight = wdst.data_ptr()
             self._keep += [wsrc, wdst]
             if s.bias is not None:
-                b = s.bias.to(dev, torch.float32).contiguous()
+                b = torch.zeros(cout, dtype=torch.float32, device=dev)
+                b[:w_cout] = s.bias.to(dev, torch.float32)
                 op.bias = b.data_ptr()
                 self._keep.append(b)
             op.act, op.post = ACT[s.act], POST[s.post]
@@ -335,7 +353,8 @@ class Plan:
             if s.gate is not None:
                 op.gate = s.gate.fmap()
             if s.out_scale is not None:
-                sc = s.out_scale.to(dev, torch.float32).contiguous()
+                sc = torch.ones(cout, dtype=torch.float32, device=dev)
+                sc[:s.out_scale.numel()] = s.out_scale.to(dev, torch.float32)
                 op.out_scale = sc.data_ptr()
                 self._keep.append(sc)
         torch.cuda.current_stream().synchronize()
@@ -346,7 +365,9 @@ class Plan:
 
     @property
     def out_fmap(self):
-        return self.dst.fmap()
+        fm = self.dst.fmap()
+        fm.c = self.out_c              # hide the zero-weight padding channels
+        return fm
 
     def run(self):
         L = _lib.lib()
@@ -357,7 +378,9 @@ class Plan:
         f = 0
         for s in self.stages:
             px = s.dst.h * s.dst.w if s.kind == 0 else s.src.h * s.src.w
-            f += 2 * s.k * s.k * s.src.c * s.dst.c * px
+            w_cout, w_cin = (s.weight.shape[0], s.weight.shape[1]) if s.kind == 0 \
+                else (s.weight.shape[1], s.weight.shape[0])
+            f += 2 * s.k * s.k * w_cin * w_cout * px
             if s.gdn is not None:
                 f += 2 * s.dst.c * s.dst.c * s.dst.h * s.dst.w
         return f

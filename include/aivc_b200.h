@@ -102,11 +102,14 @@ int aivc_profile_read(double *out);
 
 /* ---- convolution stack ------------------------------------------------------------- */
 /* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or
- * ConvTranspose2d [cin][cout][k][k] fp32 (device).  dst: SIMT [k*k][cin][cout] fp32,
- * TC [k*k][cout_pad][cin_pad] bf16.  Returns bytes written through *dst_bytes. */
+ * ConvTranspose2d [cin][cout][k][k] fp32 (device).  dst: SIMT [k*k][cin_pad][cout_pad] fp32,
+ * TC [k*k][cout_pad][cin_pad] bf16.  Weight input channel ci lands at buffer channel
+ * ci + cin_off (the layer reads a slice of a wider, zero-padded pixel); everything else is 0.
+ * `scale` multiplies every weight (1/255 when the input buffer holds 8-bit levels). */
 int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin, int cout,
-                          int engine, int cin_pad, int cout_pad, void *stream);
-size_t aivc_packed_weight_bytes(int k, int cin, int cout, int engine, int cin_pad, int cout_pad);
+                          int engine, int cin_pad, int cout_pad, int cin_off, float scale,
+                          void *stream);
+size_t aivc_packed_weight_bytes(int k, int engine, int cin_pad, int cout_pad);
 
 int aivc_conv2d_fused(const aivc_conv_op *op, void *stream);
 /* run n stages back to back on one stream (one FFI crossing per transform) */
@@ -119,16 +122,19 @@ int aivc_fill_border(const aivc_fmap *m, void *stream);
 
 /* ---- pixel ends -------------------------------------------------------------------- */
 /* InputLayer (ae_layers.py:27-35): planar 4:2:0 -> 3 channels of `dst` (Y, nearest-x2 U, V).
- * planes are uint8 (levels/255) when u8 != 0, else fp32 in [0,1]. */
-int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, const aivc_fmap *dst,
-                        void *stream);
+ * planes are uint8 levels when u8 != 0, else fp32 in [0,1].  levels != 0 stores 8-bit level
+ * units (0..255, exact in bf16; the consumer's weights carry the 1/255), else [0,1] units. */
+int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, int levels,
+                        const aivc_fmap *dst, void *stream);
 
 /* MOFNetDecoder post-processing + motion compensation + alpha split
  * (decode.py:729-739, 524-536; optical_flow.py:14-55).  mof: 6 channels (alpha, beta,
  * v_prev xy, v_next xy).  frame_is_p: beta := 1, v_next := 0.
- * pred = alpha * x_warp (3 ch), skip = (1 - alpha) * x_warp (3 ch). */
+ * pred = alpha * x_warp (3 ch, same units as prev/next), skip = (1 - alpha) * x_warp (3 ch,
+ * always [0,1] units; levels != 0 says prev/next hold 8-bit level units). */
 int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
-                    int frame_is_p, const aivc_fmap *pred, const aivc_fmap *skip, void *stream);
+                    int frame_is_p, int levels, const aivc_fmap *pred, const aivc_fmap *skip,
+                    void *stream);
 /* stand-alone motion compensation for the drop-in MotionCompensation module:
  * all tensors NCHW fp32, beta [3][h][w], flows [2][h][w]. */
 int aivc_warp_blend_nchw(const float *prev, const float *next, const float *v_prev,

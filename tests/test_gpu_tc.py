@@ -92,6 +92,24 @@ def test_wide_layers_vs_oracle(name, size, dev):
     _check(y, ref, tol)
 
 
+@pytest.mark.parametrize('name', ['conv3_s1_leaky_128', 'cheng_plain_128', 'attention_64', 'conv3_s1_relu_32_48'])
+def test_persistent_3x3_kernel_vs_oracle(name, dev):
+    """Maps large enough (>= 120 tiles of 32x8) for the persistent 3x3 kernel: odd sizes, partial
+    tiles on both edges, residual / gate / post-activation epilogues, several tiles per CTA."""
+    import aivc_b200.layers as M
+    from aivc_b200 import plan
+    from oracle import nn_ref as R
+    mk, cin, tol = WIDE[name]
+    torch.manual_seed(11)
+    m = mk(M).eval()
+    for h, w in ((135, 243), (270, 481)):
+        x = torch.randn(1, cin, h, w, generator=torch.Generator().manual_seed(h))
+        with torch.no_grad():
+            ref = R.forward_module(m, x).numpy()
+        y = plan.run_module(m, x.to(dev), _cfg()).cpu().numpy()
+        _check(y, ref, tol)
+
+
 def test_codec_bf16_closed_loop(golden_dir, dev):
     """bf16 engine on the golden system case: decoder reproduces the encoder bit for bit, and
     the reconstruction stays within a few 8-bit levels of the fp32 oracle."""
