@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[NSTAGES], bar_empty[NSTAGES], bar_acc, bar_gamma, bar_xsq, bar_norm;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[256], sscale[256], sbeta[128];
 
     uint8_t *tiles = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *xsq_tile = tiles + NSTAGES * p.stage_bytes;                 // [chunks][128][kg] bf16
@@ -87,6 +88,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
+    if (p.gdn) stage_vec(sbeta, p.gdn_beta, N, 0.f, tid, NTHREADS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -161,9 +165,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
         const int oy = my * p.out_step + ph.out_py, ox = mx * p.out_step + ph.out_px;
         const bool valid = (my < p.mh) && (mx < p.mw) && (oy < p.out.h) && (ox < p.out.w);
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const bool out_vec = fmap_vec_ok(p.out);
-        const bool res_vec = p.res.data ? fmap_vec_ok(p.res) : false;
-        const bool gate_vec = p.gate.data ? fmap_vec_ok(p.gate) : false;
+        const EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, p.act_channels, p.out_scale != nullptr);
 
         mbar_wait(&bar_acc, 0);
         tc_fence_after();
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float a = v[2 * i] + p.bias[j0 + 2 * i], b = v[2 * i + 1] + p.bias[j0 + 2 * i + 1];
+                    const float a = v[2 * i] + sbias[j0 + 2 * i], b = v[2 * i + 1] + sbias[j0 + 2 * i + 1];
                     const __nv_bfloat162 b2 = __floats2bfloat162_rn(a * a, b * b);
                     w[i] = *reinterpret_cast<const uint32_t *>(&b2);
                 }
@@ -199,47 +201,24 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
             tc_fence_after();
         }
 
-        for (int j0 = 0; j0 < N; j0 += 16) {
-            float v[16];
-            tmem_ld16(tlane + (uint32_t)j0, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += p.bias ? p.bias[j0 + i] : 0.f;
-            if (p.gdn) {
-                float nrm[16];
+        if (p.gdn) {
+            const bool interior = ctx.out.pad == 0 || (oy > 0 && oy < p.out.h - 1 && ox > 0 && ox < p.out.w - 1);
+            const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
+#pragma unroll 1
+            for (int j0 = 0; j0 < N; j0 += 16) {
+                float v[16], nrm[16];
+                tmem_ld16(tlane + (uint32_t)j0, v);
                 tmem_ld16(tlane + (uint32_t)(N + j0), nrm);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float s = sqrtf(nrm[i] + p.gdn_beta[j0 + i]);
-                    v[i] = (p.gdn == 1) ? v[i] / s : v[i] * s;
+                    const float x = v[i] + sbias[j0 + i];
+                    const float s = sqrtf(nrm[i] + sbeta[j0 + i]);
+                    v[i] = (p.gdn == 1) ? x / s : x * s;
                 }
-            } else if (p.act != AIVC_ACT_NONE) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (p.act_channels == 0 || j0 + i < p.act_channels) v[i] = act_apply(p.act, v[i]);
+                if (valid) epi_tail16(v, ctx, sscale, oy, ox, j0, interior, out_elem);
             }
-            if (valid) {
-                if (p.gate.data) {
-                    float g[16];
-                    load16(p.gate, gate_vec, oy, ox, j0, 16, g);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= g[i];
-                }
-                if (p.res.data) {
-                    float r[16];
-                    load16(p.res, res_vec, oy, ox, j0, 16, r);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += r[i];
-                }
-                if (p.post != AIVC_POST_NONE) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = post_apply(p.post, v[i]);
-                }
-                if (p.out_scale) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= p.out_scale[j0 + i];
-                }
-                store16(p.out, out_vec, oy, ox, j0, 16, v);
-            }
+        } else {
+            epi_row_dispatch(p.act, tlane, N, sbias, sscale, ctx, oy, ox, valid);
         }
         tc_fence_before();
     }

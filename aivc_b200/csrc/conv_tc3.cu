@@ -11,15 +11,16 @@
 //     tap ky of sub-tile j is just the descriptor start address + (ky + 16 j) atoms -- always
 //     1024-byte aligned, so no descriptor tricks.  Activation traffic drops 2.6x;
 //   * the CTA is persistent: accumulators are double-buffered in TMEM (2 x 256 columns), the
-//     four epilogue warps drain tile i while the MMA thread works on tile i + 1.
+//     eight epilogue warps drain tile i while the MMA thread works on tile i + 1.
 // Per 256 pixels: A 6 x 34 KB + B 18 x 16 KB = 492 KB of L2 reads (generic kernel: 1152 KB).
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 using namespace tcgen;
 
 namespace {
 
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;       // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int NA = 3;                 // activation-unit ring
 constexpr int NB = 6;                 // weight-slice ring
 constexpr int TILE_H = 32, TILE_W = 8;
@@ -33,6 +34,7 @@ struct Tc3Params {
     int tiles_x, ntiles;
     int in_pad;
     uint32_t b_bytes, b_slot;         // weight slice bytes (cout * 128) and its 1 KB-rounded slot
+    int dbg;                          // AIVC_TC3_DBG bits: timing experiments only (wrong results)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[128], sscale[128];
 
     uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *b_ring = a_ring + NA * A_UNIT;
@@ -51,7 +54,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     if (tid == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -61,6 +64,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -76,15 +81,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                     for (int kx = 0; kx < 3; ++kx) {
                         const uint32_t sa = ia % NA;
                         mbar_wait(&a_empty[sa], ((ia / NA) & 1u) ^ 1u);
+                        if (p.dbg & 8) mbar_arrive(&a_full[sa]);
+                        else {
                         mbar_expect_tx(&a_full[sa], A_UNIT);
                         tma_load_3d(a_ring + sa * A_UNIT, &tmA, &a_full[sa], kc * 64,
                                     x0 + kx - 1 + p.in_pad, y0 - 1 + p.in_pad);
+                        }
                         ++ia;
                         for (int ky = 0; ky < 3; ++ky) {
                             const uint32_t sb = ib % NB;
                             mbar_wait(&b_empty[sb], ((ib / NB) & 1u) ^ 1u);
+                            if (p.dbg & 16) mbar_arrive(&b_full[sb]);
+                            else {
                             mbar_expect_tx(&b_full[sb], p.b_bytes);
                             tma_load_3d(b_ring + sb * p.b_slot, &tmB, &b_full[sb], kc * 64, 0, ky * 3 + kx);
+                            }
                             ++ib;
                         }
                     }
@@ -112,6 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                             mbar_wait(&b_full[sb], (ib / NB) & 1u);
                             tc_fence_after();
                             const uint64_t bdesc = make_desc(smem_u32(b_ring + sb * p.b_slot), 128);
+                            if (!(p.dbg & 4))
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const uint64_t adesc = make_desc(a_addr + (uint32_t)(ky + 16 * j) * 1024u, 128);
@@ -131,59 +143,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;
+        // ===================== epilogue (warps 2..9) =====================
+        // warp w reads TMEM lanes 32*(w%4).. of sub-tile j = (w-2)/4
+        const int quarter = warp & 3, j = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        const bool out_vec = fmap_vec_ok(p.out);
-        const bool res_vec = p.res.data ? fmap_vec_ok(p.res) : false;
-        const bool gate_vec = p.gate.data ? fmap_vec_ok(p.gate) : false;
+        const EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, p.act_channels, p.out_scale != nullptr);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u;
             const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
             mbar_wait(&acc_full[buf], (it >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-                const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
-                const bool valid = (oy < p.out.h) && (ox < p.out.w);
-                const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256u + (uint32_t)(j * 128);
-#pragma unroll 1
-                for (int j0 = 0; j0 < N; j0 += 16) {
-                    float v[16];
-                    tmem_ld16(tl + (uint32_t)j0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += p.bias ? p.bias[j0 + i] : 0.f;
-                    if (p.act != AIVC_ACT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (p.act_channels == 0 || j0 + i < p.act_channels) v[i] = act_apply(p.act, v[i]);
-                    }
-                    if (valid) {
-                        if (p.gate.data) {
-                            float g[16];
-                            load16(p.gate, gate_vec, oy, ox, j0, 16, g);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= g[i];
-                        }
-                        if (p.res.data) {
-                            float r[16];
-                            load16(p.res, res_vec, oy, ox, j0, 16, r);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += r[i];
-                        }
-                        if (p.post != AIVC_POST_NONE) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = post_apply(p.post, v[i]);
-                        }
-                        if (p.out_scale) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] *= p.out_scale[j0 + i];
-                        }
-                        store16(p.out, out_vec, oy, ox, j0, 16, v);
-                    }
-                }
-            }
+            const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
+            const bool valid = (oy < p.out.h) && (ox < p.out.w);
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256u + (uint32_t)(j * 128);
+            if (!(p.dbg & 2)) epi_row_dispatch(p.act, tl, N, sbias, sscale, ctx, oy, ox, valid);
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
         }
@@ -222,6 +196,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.tiles_x = tiles_x; p.ntiles = ntiles; p.in_pad = op->in.pad;
     p.b_bytes = (uint32_t)cout * 128u;
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
+    { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
 
     const aivc_fmap &in = op->in;
     const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;

@@ -169,6 +169,128 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
     }
 }
 
+// ------------------------------------------------------------------------------------ fused epilogue
+// One accumulator row (= one output pixel, N channels) from TMEM to global memory:
+//   out = post( act(acc + bias) * gate + residual ) * out_scale
+// Everything that does not depend on the element (activation kind, presence of gate / residual /
+// scale, vector alignment, border replication) is decided once per row, outside the channel loop;
+// bias and scale are read from shared memory as broadcast float4.
+struct EpiCtx {
+    FMap out, res, gate;
+    int post, act_channels;
+    bool has_scale, out_vec, res_vec, gate_vec;
+};
+
+__device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, const FMap &gate, int post,
+                                           int act_channels, bool has_scale) {
+    EpiCtx c;
+    c.out = out; c.res = res; c.gate = gate; c.post = post; c.act_channels = act_channels;
+    c.has_scale = has_scale;
+    c.out_vec = fmap_vec_ok(out);
+    c.res_vec = res.data ? fmap_vec_ok(res) : false;
+    c.gate_vec = gate.data ? fmap_vec_ok(gate) : false;
+    return c;
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int j0, int act_channels) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(sbias + j0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b = b4[q];
+        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+    if (ACT != AIVC_ACT_NONE) {
+        if (act_channels == 0 || j0 + 16 <= act_channels) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = act_apply(ACT, v[i]);
+        } else if (j0 < act_channels) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (j0 + i < act_channels) v[i] = act_apply(ACT, v[i]);
+        }
+    }
+}
+
+// vectorised 16-channel store at a precomputed element offset (interior pixel, no replicas)
+__device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const float *v) {
+    if (m.dtype == AIVC_F32) {
+        float4 *q = reinterpret_cast<float4 *>((float *)m.data + elem);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+        }
+        uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem);
+        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+__device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
+                                           int j0, bool interior, size_t out_elem) {
+    if (c.gate.data) {
+        float g[16];
+        load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= g[i];
+    }
+    if (c.res.data) {
+        float r[16];
+        load16(c.res, c.res_vec, oy, ox, j0, 16, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
+    }
+    if (c.post != AIVC_POST_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = post_apply(c.post, v[i]);
+    }
+    if (c.has_scale) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sscale + j0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 s = s4[q];
+            v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
+        }
+    }
+    if (interior && c.out_vec) store16_at(c.out, out_elem + j0, v);
+    else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
+                                        const EpiCtx &c, int oy, int ox, bool valid) {
+    const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
+    const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < N; j0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)j0, v);
+        epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
+        if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem);
+    }
+}
+
+__device__ __forceinline__ void epi_row_dispatch(int act, uint32_t taddr, int N, const float *sbias,
+                                                 const float *sscale, const EpiCtx &c, int oy, int ox,
+                                                 bool valid) {
+    switch (act) {
+        case AIVC_ACT_LEAKY: epi_row<AIVC_ACT_LEAKY>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
+        case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
+        case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
+        default: epi_row<AIVC_ACT_NONE>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
+    }
+}
+
+// bias / scale staged once per CTA in shared memory (zeros / ones when absent)
+__device__ __forceinline__ void stage_vec(float *dst, const float *src, int n, float fill, int tid, int nthreads) {
+    for (int i = tid; i < n; i += nthreads) dst[i] = src ? src[i] : fill;
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
