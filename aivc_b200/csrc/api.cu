@@ -11,7 +11,7 @@ unsigned long long g_aivc_launches = 0;
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every conv stage
 #include <vector>
-struct StageRec { cudaEvent_t a, b; int engine; double flops; };
+struct StageRec { cudaEvent_t a, b; int engine; double flops; int kind, k, stride, cin, cout, h, w, act; };
 static std::vector<StageRec> g_prof;
 static bool g_prof_on = false;
 
@@ -79,6 +79,8 @@ int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
         AIVC_CHECK_CUDA(cudaEventCreate(&r.b));
         r.engine = op->engine;
         r.flops = stage_flops(op);
+        r.kind = op->kind; r.k = op->k; r.stride = op->stride; r.cin = op->in.c; r.cout = op->out.c;
+        r.h = op->out.h; r.w = op->out.w; r.act = op->act;
         AIVC_CHECK_CUDA(cudaEventRecord(r.a, (cudaStream_t)stream));
     }
     const int rc = op->engine == AIVC_ENGINE_SIMT ? conv_simt_run(op, (cudaStream_t)stream)
@@ -96,6 +98,21 @@ int aivc_profile_enable(int on) {
     for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
     g_prof_on = on != 0;
+    return 0;
+}
+
+// one CSV line per recorded stage: engine,kind,k,stride,cin,cout,out_h,out_w,act,flops,ms
+int aivc_profile_dump(const char *path) {
+    FILE *f = fopen(path, "w");
+    if (!f) AIVC_FAIL("profile_dump: cannot open %s", path);
+    fprintf(f, "engine,kind,k,stride,cin,cout,out_h,out_w,act,flops,ms\n");
+    for (auto &r : g_prof) {
+        AIVC_CHECK_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.0f,%.6f\n", r.engine, r.kind, r.k, r.stride, r.cin, r.cout, r.h, r.w, r.act, r.flops, ms);
+    }
+    fclose(f);
     return 0;
 }
 

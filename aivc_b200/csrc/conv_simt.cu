@@ -29,11 +29,14 @@ struct SimtParams {
     int gdn_mode;             // 0 none, 1 x / sqrt(v), 2 x * sqrt(v)  (x read from gx)
     int clamp;                // 1 replicate (conv), 0 zero outside (transposed conv)
     int in_step;              // input coordinate = m * in_step + dy
-    int out_step, out_py, out_px;   // output coordinate = m * out_step + out_p
+    int out_step;             // output coordinate = m * out_step + phase offset
     int mh, mw;               // size of the m-grid handled by this launch
-    int ntaps;
-    signed char dy[MAX_TAPS], dx[MAX_TAPS];
-    unsigned char widx[MAX_TAPS];
+    int nphase;               // blockIdx.z selects the output phase (transposed conv: 4)
+    struct Phase {
+        int ntaps, out_py, out_px;
+        signed char dy[MAX_TAPS], dx[MAX_TAPS];
+        unsigned char widx[MAX_TAPS];
+    } ph[4];
 };
 
 __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
@@ -41,6 +44,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
     __shared__ float Bs[BK][BN + 4];
 
     const int tid = threadIdx.x;
+    const SimtParams::Phase &ph = p.ph[blockIdx.z];
     const int tiles_x = (p.mw + 7) / 8;
     const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x % tiles_x;
     const int n0 = blockIdx.y * BN;
@@ -57,9 +61,9 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
     const int lmy = tile_y * 8 + lp / 8, lmx = tile_x * 8 + lp % 8;
     const bool lvalid = (lmy < p.mh) && (lmx < p.mw);
 
-    for (int t = 0; t < p.ntaps; ++t) {
-        int iy = lmy * p.in_step + p.dy[t];
-        int ix = lmx * p.in_step + p.dx[t];
+    for (int t = 0; t < ph.ntaps; ++t) {
+        int iy = lmy * p.in_step + ph.dy[t];
+        int ix = lmx * p.in_step + ph.dx[t];
         bool inb = lvalid;
         if (p.clamp) {
             iy = min(max(iy, 0), p.in.h - 1);
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
         } else {
             inb = inb && iy >= 0 && iy < p.in.h && ix >= 0 && ix < p.in.w;
         }
-        const float *wt = p.w + (size_t)p.widx[t] * p.cin * p.cout;
+        const float *wt = p.w + (size_t)ph.widx[t] * p.cin * p.cout;
         for (int c0 = 0; c0 < p.cin; c0 += BK) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
         const int pp = ty * 4 + i;
         const int my = tile_y * 8 + pp / 8, mx = tile_x * 8 + pp % 8;
         if (my >= p.mh || mx >= p.mw) continue;
-        const int oy = my * p.out_step + p.out_py, ox = mx * p.out_step + p.out_px;
+        const int oy = my * p.out_step + ph.out_py, ox = mx * p.out_step + ph.out_px;
         if (oy >= p.out.h || ox >= p.out.w) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const SimtParams p) {
 }
 
 int launch(const SimtParams &p, cudaStream_t st) {
-    dim3 grid(ceil_div(p.mh, 8) * ceil_div(p.mw, 8), ceil_div(p.cout, BN));
+    dim3 grid(ceil_div(p.mh, 8) * ceil_div(p.mw, 8), ceil_div(p.cout, BN), p.nphase);
     conv_simt_kernel<<<grid, NT, 0, st>>>(p);
     AIVC_CHECK_LAUNCH("conv_simt_kernel");
     return 0;
@@ -182,13 +186,14 @@ int conv_simt_run(const aivc_conv_op *op, cudaStream_t st) {
         p.in_step = op->stride;
         p.out_step = 1;
         p.mh = op->out.h; p.mw = op->out.w;
-        p.ntaps = k * k;
+        p.nphase = 1;
+        p.ph[0].ntaps = k * k;
         for (int ky = 0; ky < k; ++ky)
             for (int kx = 0; kx < k; ++kx) {
                 const int t = ky * k + kx;
-                p.dy[t] = (signed char)(ky - k / 2);
-                p.dx[t] = (signed char)(kx - k / 2);
-                p.widx[t] = (unsigned char)t;
+                p.ph[0].dy[t] = (signed char)(ky - k / 2);
+                p.ph[0].dx[t] = (signed char)(kx - k / 2);
+                p.ph[0].widx[t] = (unsigned char)t;
             }
         if (launch(p, st)) return 1;
     } else {
@@ -197,23 +202,25 @@ int conv_simt_run(const aivc_conv_op *op, cudaStream_t st) {
         p.in_step = 1;
         p.out_step = 2;
         p.mh = op->in.h; p.mw = op->in.w;
+        p.nphase = 4;                              // the four output parities in one launch
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px) {
+                SimtParams::Phase &ph = p.ph[py * 2 + px];
                 int n = 0;
                 for (int ky = 0; ky < k; ++ky) {
                     if ((py + pad - ky) & 1) continue;
                     for (int kx = 0; kx < k; ++kx) {
                         if ((px + pad - kx) & 1) continue;
-                        p.dy[n] = (signed char)((py + pad - ky) / 2);
-                        p.dx[n] = (signed char)((px + pad - kx) / 2);
-                        p.widx[n] = (unsigned char)(ky * k + kx);
+                        ph.dy[n] = (signed char)((py + pad - ky) / 2);
+                        ph.dx[n] = (signed char)((px + pad - kx) / 2);
+                        ph.widx[n] = (unsigned char)(ky * k + kx);
                         ++n;
                     }
                 }
-                p.ntaps = n;
-                p.out_py = py; p.out_px = px;
-                if (launch(p, st)) return 1;
+                ph.ntaps = n;
+                ph.out_py = py; ph.out_px = px;
             }
+        if (launch(p, st)) return 1;
     }
 
     if (has_gdn) {
@@ -233,7 +240,8 @@ int conv_simt_run(const aivc_conv_op *op, cudaStream_t st) {
         if (op->gate.data) g.gate = to_dev(op->gate);
         g.clamp = 1; g.in_step = 1; g.out_step = 1;
         g.mh = op->out.h; g.mw = op->out.w;
-        g.ntaps = 1; g.dy[0] = 0; g.dx[0] = 0; g.widx[0] = 0;
+        g.nphase = 1;
+        g.ph[0].ntaps = 1; g.ph[0].dy[0] = 0; g.ph[0].dx[0] = 0; g.ph[0].widx[0] = 0;
         if (launch(g, st)) return 1;
     }
     return 0;

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int MAX_TAPS = 25;
 constexpr int NTHREADS = 192;
-constexpr int NSTAGES = 3;
+constexpr int MAX_STAGES = 8;
 
 struct Phase {
     int ntaps, out_py, out_px, _pad;
@@ -43,25 +43,27 @@ struct TcParams {
     int tw, th, tiles_x;
     int mh, mw, out_step, mode;                  // mode 0: 3-D map, 1: 5-D map
     int tmem_cols, kg;                           // kg: columns per swizzle atom of the GDN operands
+    int nstages, xsq_off;                        // pipeline depth; byte offset of the x^2 operand tile
     uint32_t stage_bytes, a_bytes, b_bytes;
     Phase ph[4];
 };
 
 // ------------------------------------------------------------------------------------ kernel
 template <int BK>
-__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmG,
                                                            const TcParams p) {
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[NSTAGES], bar_empty[NSTAGES], bar_acc, bar_gamma, bar_xsq, bar_norm;
+    __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc, bar_gamma, bar_xsq, bar_norm;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[256], sscale[256], sbeta[128];
 
     uint8_t *tiles = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *xsq_tile = tiles + NSTAGES * p.stage_bytes;                 // [chunks][128][kg] bf16
-    uint8_t *gam_tile = xsq_tile + 128 * p.cout * 2;                     // [chunks][N][kg] bf16
+    const int NSTAGES = p.nstages;
+    uint8_t *xsq_tile = tiles + p.xsq_off;            // [chunks][128][kg] bf16; may alias the (drained) stage ring
+    uint8_t *gam_tile = tiles + (size_t)NSTAGES * p.stage_bytes + (p.xsq_off ? 128 * p.cout * 2 : 0);   // [chunks][N][kg]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Phase &ph = p.ph[blockIdx.z];
@@ -212,8 +214,9 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float x = v[i] + sbias[j0 + i];
-                    const float s = sqrtf(nrm[i] + sbeta[j0 + i]);
-                    v[i] = (p.gdn == 1) ? x / s : x * s;
+                    const float t = nrm[i] + sbeta[j0 + i];
+                    const float rs = rsqrtf(t);                 // MUFU.RSQ: 2^-22 relative, far below bf16
+                    v[i] = (p.gdn == 1) ? x * rs : x * (t * rs);
                 }
                 if (valid) epi_tail16(v, ctx, sscale, oy, ox, j0, interior, out_elem);
             }
@@ -370,13 +373,29 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)cout, 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, rowb, "B")) return 1;
     }
-    size_t smem = 1024 + (size_t)NSTAGES * p.stage_bytes;
+    // Pipeline depth.  Two CTAs per SM (<= ~110 KB each) let one CTA's epilogue hide behind the
+    // other's main loop; grids that cannot fill the chip twice get one deep pipeline instead.
+    const int nctas = p.tiles_x * tiles_y * nphase;
+    const size_t gam_bytes = gdn ? (size_t)cout * cout * 2 : 0;
+    const size_t xsq_bytes = gdn ? (size_t)128 * cout * 2 : 0;
+    (void)nctas;
+    const size_t budget = 110 * 1024;               // always two CTAs per SM (also keeps the smem carve-out stable)
+    int nst = (int)((budget - 1024 - gam_bytes) / p.stage_bytes);
+    if (nst > MAX_STAGES) nst = MAX_STAGES;
+    if (BK == 64 && nst > 3) nst = 3;               // measured: deeper 16 KB-stage rings only add L2 pressure
+    if (nst < 2) nst = 2;
+    p.nstages = nst;
+    p.xsq_off = 0;                                   // x^2 tile aliases the stage ring ...
+    size_t smem = 1024 + (size_t)nst * p.stage_bytes + gam_bytes;
+    if (gdn && (size_t)nst * p.stage_bytes < xsq_bytes) {          // ... unless the ring is too small
+        p.xsq_off = nst * (int)p.stage_bytes;
+        smem += xsq_bytes;
+    }
     if (gdn) {
         cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};
         cuuint64_t strides[1] = {(cuuint64_t)cout * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.kg, (cuuint32_t)cout};
         if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, p.kg * 2, "gamma")) return 1;
-        smem += (size_t)128 * cout * 2 + (size_t)cout * cout * 2;
     }
     if (smem > 220 * 1024) AIVC_FAIL("conv_tc: %zu bytes of shared memory needed", smem);
     dim3 grid(p.tiles_x * tiles_y, 1, nphase);

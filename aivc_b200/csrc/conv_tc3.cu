@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u;
             const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
-            mbar_wait(&acc_full[buf], (it >> 1) & 1u);
-            tc_fence_after();
             const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
             const bool valid = (oy < p.out.h) && (ox < p.out.w);
+            mbar_wait(&acc_full[buf], (it >> 1) & 1u);
+            tc_fence_after();
             const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256u + (uint32_t)(j * 128);
             if (!(p.dbg & 2)) epi_row_dispatch(p.act, tl, N, sbias, sscale, ctx, oy, ox, valid);
             tc_fence_before();
@@ -183,7 +183,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->in.dtype != AIVC_BF16 || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 8) return -1;
     const int tiles_x = ceil_div(op->out.w, TILE_W), tiles_y = ceil_div(op->out.h, TILE_H);
     const int ntiles = tiles_x * tiles_y;
-    if (ntiles < 120) return -1;            // small maps: the 128-pixel-tile kernel fills more SMs
+    if (ntiles < 296) return -1;            // < 2 tiles per SM: the 128-pixel-tile kernel fills the chip better
 
     Tc3Params p;
     memset(&p, 0, sizeof(p));

@@ -232,14 +232,24 @@ __device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const flo
 }
 
 __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
-                                           int j0, bool interior, size_t out_elem) {
+                                           int j0, bool interior, size_t out_elem, const uint4 *rb = nullptr) {
     if (c.gate.data) {
         float g[16];
         load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= g[i];
     }
-    if (c.res.data) {
+    if (rb) {                       // residual row prefetched as packed bf16 (see res_prefetch)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t w[4] = {rb[h].x, rb[h].y, rb[h].z, rb[h].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[8 * h + 2 * q] += __uint_as_float(w[q] << 16);
+                v[8 * h + 2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+            }
+        }
+    } else if (c.res.data) {
         float r[16];
         load16(c.res, c.res_vec, oy, ox, j0, 16, r);
 #pragma unroll
@@ -261,17 +271,34 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
     else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
 }
 
+// 16 channels of a residual row as packed bf16 (two 16-byte loads), for software pipelining
+__device__ __forceinline__ void res_fetch16(const EpiCtx &c, size_t res_elem, int j0, uint4 *rb) {
+    const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)c.res.data + res_elem + j0);
+    rb[0] = p[0];
+    rb[1] = p[1];
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
                                         const EpiCtx &c, int oy, int ox, bool valid) {
     const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
     const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
+    // bf16 residual rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
+    // the TMEM load and arithmetic of chunk j
+    const bool pipe_res = valid && c.res.data && c.res_vec && c.res.dtype == AIVC_BF16;
+    const size_t res_elem = pipe_res ? fm_index(c.res, oy, ox, 0) : 0;
+    uint4 rb[2], rn[2];
+    if (pipe_res) res_fetch16(c, res_elem, 0, rn);
 #pragma unroll 1
     for (int j0 = 0; j0 < N; j0 += 16) {
+        if (pipe_res) {
+            rb[0] = rn[0]; rb[1] = rn[1];
+            if (j0 + 16 < N) res_fetch16(c, res_elem, j0 + 16, rn);
+        }
         float v[16];
         tmem_ld16(taddr + (uint32_t)j0, v);
         epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
-        if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem);
+        if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem, pipe_res ? rb : nullptr);
     }
 }
 

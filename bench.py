@@ -236,6 +236,8 @@ def run_ours(args):
             out = (C.c_double * 6)()
             _lib.check(L.aivc_profile_read(out))
             prof = list(out)
+            if args.stage_csv and rank == 0:
+                _lib.check(L.aivc_profile_dump(args.stage_csv.encode()))
             L.aivc_profile_enable(0)
         launches = L.aivc_launch_count() - l0
         if world > 1:
@@ -301,6 +303,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stage-csv', default='', help='dump per-stage CUDA-event timings of the timed region')
     args = ap.parse_args()
     import __graft_entry__ as g
     if int(os.environ.get('LOCAL_RANK', '0')) == 0:

@@ -99,6 +99,8 @@ const char *aivc_last_error(void);
 unsigned long long aivc_launch_count(void);
 int aivc_profile_enable(int on);
 int aivc_profile_read(double *out);
+/* one CSV line per recorded stage (engine, geometry, flops, ms) */
+int aivc_profile_dump(const char *path);
 
 /* ---- convolution stack ------------------------------------------------------------- */
 /* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or
