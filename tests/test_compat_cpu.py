@@ -1,0 +1,118 @@
+"""CPU suite: bitstream container known answers (bytes produced by the reference's own
+header.py / cat_binary_files.py for the same inputs, captured when the fixtures were made),
+module-path aliases for un-pickling, the torchac shim, and 2-rank GOP sharding over gloo."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+from aivc_b200 import container as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# reference output of write_gop_header + cat_one_gop + cat_one_video for frames 3,4,5 =
+# b'abc'*5, b'', b'xyz'; '1_GOP_2'; idx_rate 0.5; dims (1080,1920)/(68,120)/(17,30)
+GOP_KAT = '0000010002080000000f616263616263616263616263616263000000000000000378797a'
+VIDEO_KAT = ('04380780004400780011001e00010003000500000024' + GOP_KAT)
+
+
+def test_container_known_answers():
+    g = K.pack_gop('1_GOP_2', [b'abc' * 5, b'', b'xyz'], 0.5)
+    assert g.hex() == GOP_KAT
+    v = K.pack_video((1080, 1920), (68, 120), (17, 30), [g], 3, 5)
+    assert v.hex() == VIDEO_KAT
+    dims, gops, first, last = K.unpack_video(v)
+    assert dims == {'x': (1080, 1920), 'y': (68, 120), 'z': (17, 30), 'x_uv': (540, 960)}
+    assert (first, last) == (3, 5) and gops == [g]
+    name, rate, frames = K.unpack_gop(gops[0])
+    assert (name, rate, frames) == ('1_GOP_2', 0.5, [b'abc' * 5, b'', b'xyz'])
+    assert K.parse_gop_header(K.gop_header('LDP_8')) == ('LDP_8', 0.0)
+
+
+def test_install_aliases_allow_unpickling_reference_paths():
+    from aivc_b200 import compat
+    import aivc_b200.layers as L
+    compat.install()
+    import layers.misc.custom_conv_layers as ref_path
+    assert ref_path.ChengResBlock is L.ChengResBlock
+    import models
+    assert hasattr(models, 'FullNet')
+    m = L.ChengResBlock(8, 'down')
+    # a pickle that names the REFERENCE module path must resolve to the mirror
+    saved = {}
+    for path, names in compat._MODULE_MAP.items():
+        for n in names:
+            saved[n] = getattr(L, n).__module__
+            getattr(L, n).__module__ = path
+    try:
+        blob = pickle.dumps(m)
+    finally:
+        for n, mod in saved.items():
+            getattr(L, n).__module__ = mod
+    assert b'layers.misc.custom_conv_layers' in blob and b'aivc_b200.layers' not in blob
+    m2 = pickle.loads(blob)
+    assert type(m2) is L.ChengResBlock
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert hasattr(torch, 'set_deterministic')
+
+
+def test_torchac_shim_matches_oracle_coder():
+    from aivc_b200 import compat
+    from oracle import torchac_shim as O
+    compat.install()
+    import torchac
+    g = torch.Generator().manual_seed(0)
+    cdf = torch.sort(torch.rand(200, 514, generator=g), dim=1)[0]
+    cdf[:, 0], cdf[:, -1] = 0, 1
+    sym = torch.randint(0, 512, (200,), generator=g).to(torch.int16)
+    a = torchac.encode_float_cdf(cdf, sym, check_input_bounds=True)
+    assert a == O.encode_float_cdf(cdf, sym)
+    assert torch.equal(torchac.decode_float_cdf(cdf, a), sym)
+
+
+def test_convert_swaps_reference_named_layers():
+    from aivc_b200 import compat
+    import aivc_b200.layers as L
+
+    class CustomConvLayer(torch.nn.Module):      # stands for the reference class of that name
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.Sequential(torch.nn.ReplicationPad2d(1), torch.nn.Conv2d(4, 4, 3))
+
+    holder = torch.nn.Sequential(CustomConvLayer(), torch.nn.Sequential(CustomConvLayer()))
+    w = holder[0].layers[1].weight
+    compat.convert(holder)
+    assert type(holder[0]) is L.CustomConvLayer and type(holder[1][0]) is L.CustomConvLayer
+    assert holder[0].layers[1].weight is w                    # shared, not copied
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from aivc_b200 import sharding
+dist.init_process_group('gloo')
+r, n = dist.get_rank(), dist.get_world_size()
+mine = sharding.gops_of_rank(7, r, n)
+payload = {g: bytes([g]) * (g + 1) for g in mine}
+allb = sharding.gather_gop_bytes(payload, 7)
+if r == 0:
+    assert [len(b) for b in allb] == [i + 1 for i in range(7)], allb
+    assert all(b == bytes([i]) * (i + 1) for i, b in enumerate(allb))
+    print('OK', mine)
+dist.destroy_process_group()
+'''
+
+
+def test_gop_sharding_two_ranks_gloo(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29541')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29541', str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'OK [0, 2, 4, 6]' in out.stdout
