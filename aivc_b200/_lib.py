@@ -50,6 +50,7 @@ _SIGS = {
     'aivc_nchw_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
     'aivc_fmap_to_nchw': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
     'aivc_fill_border': (C.c_int, [C.POINTER(FMap), C.c_void_p]),
+    'aivc_fmap_copy': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p]),
     'aivc_yuv420_to_fmap': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.POINTER(FMap), C.c_void_p]),
     'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int, C.c_int] + [C.POINTER(FMap)] * 2

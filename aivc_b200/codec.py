@@ -58,7 +58,7 @@ class CondNetEngine:
         self.cy, self.cz, self.csc = cy, cz, csc
         (hy, wy), (hz, wz) = latent_dims(h, w)
         self.dims_y, self.dims_z = (hy, wy), (hz, wz)
-        exact = Config(precision='fp32')           # hyperprior: exact engine (sigma steers the coder)
+        exact = cfg.hyper_cfg()                    # hyperprior engine ('fp32' keeps sigma/mu exact)
         tc = cfg.precision == 'bf16'
         embed = (lambda off: (in_buf.c, off, (1.0 / 255.0) if levels else 1.0)) if tc else (lambda off: None)
         self.g_s = Plan(net.g_s, hy, wy, cy + csc, device, cfg, pad_cout=16 if tc else 0)
@@ -68,8 +68,11 @@ class CondNetEngine:
         if getattr(net, 'g_a', None) is not None:        # a decoder-only model has no analysis side
             self.g_a = Plan(net.g_a, h, w, in_c, device, cfg, src_buf=in_buf,
                             out_scale=torch.ones(cy), in_embed=embed(0))
-            self.h_a = Plan(net.h_a, hy, wy, cy, device, exact, src_buf=self.g_a.dst.buf,
+            # y stays fp32 for the quantiser; a tensor-core h_a reads a bf16, bordered copy of it
+            self.h_a = Plan(net.h_a, hy, wy, cy, device, exact,
+                            src_buf=self.g_a.dst.buf if exact.precision == 'fp32' else None,
                             dst_into=(self.h_s.src.buf, 0), out_post='round_clamp')
+            self.y_copy = exact.precision != 'fp32' 
         if self.has_ref:
             self.g_a_ref = Plan(net.g_a_ref, h, w, ref_c, device, cfg, src_buf=in_buf,
                                 src_c_off=0 if tc else ref_off, dst_into=(self.gs_in, cy),
@@ -121,6 +124,9 @@ class CondNetEngine:
         enc_gain, dec_gain = self.gains[frame_type]
         self.g_a.ops[len(self.g_a.ops) - 1].out_scale = enc_gain.data_ptr()
         self.g_a.run()
+        if self.y_copy:
+            ys, yd = self.g_a.out_fmap, self.h_a.in_fmap
+            _lib.check(L.aivc_fmap_copy(C.byref(ys), C.byref(yd), st))
         self.h_a.run()
         zf = self.h_s.in_fmap
         _lib.check(L.aivc_fmap_to_i16(C.byref(zf), self.z_dev.data_ptr(), st))

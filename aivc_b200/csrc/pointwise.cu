@@ -32,6 +32,16 @@ __global__ void fmap_to_nchw_kernel(FMap src, float *__restrict__ dst) {
     }
 }
 
+__global__ void fmap_copy_kernel(FMap src, FMap dst) {
+    const size_t n = (size_t)dst.h * dst.w * dst.c;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % dst.c), pix = (int)(i / dst.c);
+        const int y = pix / dst.w, x = pix % dst.w;
+        fm_store(dst, y, x, ch, fm_load(src, y, x, ch));
+    }
+}
+
 __global__ void fill_border_kernel(FMap m) {
     // one thread per padded pixel of the border ring
     const int hp = m.h + 2 * m.pad, wp = m.w + 2 * m.pad;
@@ -298,6 +308,34 @@ __global__ void dequantize_latent_kernel(const int16_t *__restrict__ q, FMap hs,
     }
 }
 
+// ---------------------------------------------------------------- transposed conv as GEMM + col2im
+// The narrow output layers (ConvTranspose2d k5, 128 -> 3 or 6 channels; custom_conv_layers.py:214-224)
+// are computed as P[pixel][(ky,kx,co)] = in[pixel][:] . W[:, co, ky, kx] on the tensor cores (a 1x1
+// stage with 25*co output channels), after which every P element belongs to exactly one output
+// pixel: out[2*iy - pad + ky][2*ix - pad + kx][co] += P[iy][ix][(ky,kx,co)].  This kernel is that
+// gather (<= 9 terms per output element), plus bias and activation.
+__global__ void col2im_tconv_kernel(FMap P, FMap out, const float *__restrict__ bias, int k, int act) {
+    const int co_n = out.c, pad = (k + 1) / 2 - 1;
+    const size_t n = (size_t)out.h * out.w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int oy = (int)(i / out.w), ox = (int)(i % out.w);
+        float acc[8];
+        for (int c = 0; c < co_n; ++c) acc[c] = bias ? bias[c] : 0.f;
+        for (int ky = (oy + pad) & 1; ky < k; ky += 2) {
+            const int iy = (oy + pad - ky) / 2;
+            if (oy + pad - ky < 0 || iy >= P.h) continue;
+            for (int kx = (ox + pad) & 1; kx < k; kx += 2) {
+                const int ix = (ox + pad - kx) / 2;
+                if (ox + pad - kx < 0 || ix >= P.w) continue;
+                const int base = (ky * k + kx) * co_n;
+                for (int c = 0; c < co_n; ++c) acc[c] += fm_load(P, iy, ix, base + c);
+            }
+        }
+        for (int c = 0; c < co_n; ++c) fm_store(out, oy, ox, c, act_apply(act, acc[c]));
+    }
+}
+
 // ---------------------------------------------------------------- weight re-layout
 __global__ void pack_weight_kernel(const float *__restrict__ src, void *__restrict__ dst, int kind,
                                    int k, int cin, int cout, int engine, int cin_pad, int cout_pad,
@@ -334,6 +372,16 @@ int grid_for(size_t n) {
 
 }  // namespace
 
+int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
+    if (op->out.c > 8) AIVC_FAIL("col2im: at most 8 output channels, got %d", op->out.c);
+    if (op->in.c < op->k * op->k * op->out.c) AIVC_FAIL("col2im: input has %d channels, needs %d", op->in.c, op->k * op->k * op->out.c);
+    if (op->out.h != 2 * op->in.h || op->out.w != 2 * op->in.w) AIVC_FAIL("col2im: output must be exactly 2x");
+    col2im_tconv_kernel<<<grid_for((size_t)op->out.h * op->out.w), PT, 0, st>>>(to_dev(op->in), to_dev(op->out), op->bias,
+                                                                                op->k, op->act);
+    AIVC_CHECK_LAUNCH("col2im_tconv");
+    return 0;
+}
+
 extern "C" {
 
 int aivc_nchw_to_fmap(const float *src, const aivc_fmap *dst, void *stream) {
@@ -349,6 +397,15 @@ int aivc_fmap_to_nchw(const aivc_fmap *src, float *dst, void *stream) {
     fmap_to_nchw_kernel<<<grid_for((size_t)src->h * src->w * src->c), PT, 0, (cudaStream_t)stream>>>(
         to_dev(*src), dst);
     AIVC_CHECK_LAUNCH("fmap_to_nchw");
+    return 0;
+}
+
+int aivc_fmap_copy(const aivc_fmap *src, const aivc_fmap *dst, void *stream) {
+    if (validate_fmap(src, "fmap_copy src") || validate_fmap(dst, "fmap_copy dst")) return 1;
+    if (src->h != dst->h || src->w != dst->w || src->c != dst->c) AIVC_FAIL("fmap_copy: shape mismatch");
+    fmap_copy_kernel<<<grid_for((size_t)dst->h * dst->w * dst->c), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*src), to_dev(*dst));
+    AIVC_CHECK_LAUNCH("fmap_copy");
     return 0;
 }
 

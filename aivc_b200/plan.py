@@ -35,9 +35,15 @@ class Config:
     precision: str = 'bf16'        # 'fp32': every stage on the exact SIMT engine, fp32 buffers
                                    # 'bf16': tcgen05 engine wherever the channel counts allow
     tc_min_cin: int = 16           # tensor-core stages need cin % 16 == 0 and cout % 16 == 0
+    hyper: str = 'auto'            # precision of h_a / h_s: 'fp32' (exact engine), 'bf16', or
+                                   # 'auto' = same as `precision`
 
     def key(self):
-        return (self.precision, self.tc_min_cin)
+        return (self.precision, self.tc_min_cin, self.hyper)
+
+    def hyper_cfg(self):
+        h = self.precision if self.hyper == 'auto' else self.hyper
+        return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h)
 
 
 DEFAULT = Config()
@@ -243,9 +249,11 @@ class Plan:
                 if s.src is self.src:
                     s.cin_off, s.w_scale = off, wsc
             self.src.c = buf_c
+        if cfg.precision == 'bf16':
+            self._split_narrow_tconvs()
         last = self.stages[-1]
         self.out_c = self.dst.c
-        if pad_cout and self.dst.c % pad_cout:
+        if pad_cout and self.dst.c % pad_cout and last.kind != 2:
             assert last.gdn is None and last.res is None and last.gate is None
             self.dst.c = -(-self.dst.c // pad_cout) * pad_cout
         if out_scale is not None:
@@ -257,10 +265,33 @@ class Plan:
         self._assign_buffers(src_buf, src_c_off, dst_into, in_dtype)
         self._materialize()
 
+    def _split_narrow_tconvs(self):
+        """ConvTranspose2d with a handful of output channels (the 128 -> 3/6 pixel-domain ends):
+        run the contraction as ONE 1x1 tensor-core stage producing k*k*cout channels per input
+        pixel, then scatter them to the 2x output (col2im).  Reads the wide input once instead
+        of once per tap."""
+        out = []
+        for s in self.stages:
+            cin, cout = s.weight.shape[0], s.weight.shape[1]
+            if (s.kind == 1 and cout <= 8 and s.k * s.k * cout <= 256 and cin % 16 == 0 and s.gdn is None
+                    and s.res is None and s.gate is None and s.post == 'none' and s.out_scale is None
+                    and s.cin_off == 0 and s.w_scale == 1.0):
+                kk = s.k * s.k * cout
+                wp = s.weight.permute(2, 3, 1, 0).reshape(kk, cin, 1, 1).contiguous()
+                p_t = T(s.src.h, s.src.w, -(-kk // 16) * 16)
+                out.append(Stage(0, 1, 1, s.src, p_t, wp, None, 'no'))
+                out.append(Stage(2, s.k, 2, p_t, s.dst, None, s.bias, s.act))
+            else:
+                out.append(s)
+        self.stages = out
+
     # -- engine / dtype / border selection
     def _choose_engines(self):
         tc = self.cfg.precision == 'bf16'
         for s in self.stages:
+            if s.kind == 2:
+                s.engine = ENGINE_SIMT
+                continue
             cin, cout = s.src.c, s.dst.c
             ok = tc and cin % self.cfg.tc_min_cin == 0 and cout % 16 == 0 and cout <= 256
             if s.gdn is not None and cout > 128:
@@ -322,6 +353,13 @@ class Plan:
             cin, cout = s.src.c, s.dst.c
             op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
             op.inp, op.out = s.src.fmap(), s.dst.fmap()
+            if s.kind == 2:
+                op.act = ACT[s.act]
+                if s.bias is not None:
+                    b = s.bias.to(dev, torch.float32).contiguous()
+                    op.bias = b.data_ptr()
+                    self._keep.append(b)
+                continue
             wsrc = s.weight.to(dev, torch.float32).contiguous()
             w_cout, w_cin = (wsrc.shape[0], wsrc.shape[1]) if s.kind == 0 else (wsrc.shape[1], wsrc.shape[0])
             nbytes = L.aivc_packed_weight_bytes(s.k, s.engine, cin, cout)
@@ -377,6 +415,8 @@ class Plan:
         """Algorithmic FLOPs of the reference graph: convs, tconvs and GDN 1x1."""
         f = 0
         for s in self.stages:
+            if s.kind == 2:
+                continue
             px = s.dst.h * s.dst.w if s.kind == 0 else s.src.h * s.src.w
             w_cout, w_cin = (s.weight.shape[0], s.weight.shape[1]) if s.kind == 0 \
                 else (s.weight.shape[1], s.weight.shape[0])

@@ -71,6 +71,8 @@ typedef struct {
  *           (also the bare 1x1 Conv2d's of ChengResBlock/attention: pad 0)
  *   kind 1: ConvTranspose2d(k, stride 2, pad (k+1)/2-1, output_padding 1)
  *                                                        UpscalingLayer   custom_conv_layers.py:183-253
+ *   kind 2: col2im of a transposed conv computed as GEMM: in holds k*k*cout channels
+ *           P[(ky,kx,co)] per INPUT pixel, out[2iy-pad+ky][2ix-pad+kx][co] = act(bias + sum P)
  *   out = post( act(conv(in) + bias) * gate + residual ) * out_scale
  */
 typedef struct {
@@ -121,6 +123,8 @@ int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream);
 int aivc_nchw_to_fmap(const float *src, const aivc_fmap *dst, void *stream);
 int aivc_fmap_to_nchw(const aivc_fmap *src, float *dst, void *stream);
 int aivc_fill_border(const aivc_fmap *m, void *stream);
+/* dst = src with dst's dtype, channel placement and replicate border (same h, w, c) */
+int aivc_fmap_copy(const aivc_fmap *src, const aivc_fmap *dst, void *stream);
 
 /* ---- pixel ends -------------------------------------------------------------------- */
 /* InputLayer (ae_layers.py:27-35): planar 4:2:0 -> 3 channels of `dst` (Y, nearest-x2 U, V).
