@@ -135,13 +135,51 @@ int aivc_profile_read(double *out) {
     return 0;
 }
 
+struct Lanes { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static Lanes g_lanes[16];
+
+static int lanes_for_current_device(Lanes **out) {
+    int dev = 0;
+    AIVC_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) AIVC_FAIL("device index %d out of range", dev);
+    Lanes &l = g_lanes[dev];
+    if (!l.side) {
+        AIVC_CHECK_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+        AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    }
+    *out = &l;
+    return 0;
+}
+
 int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
-    for (int i = 0; i < n; ++i)
-        if (aivc_conv2d_fused(ops + i, stream)) {
+    cudaStream_t main_s = (cudaStream_t)stream;
+    Lanes *l = nullptr;
+    bool side_dirty = false;
+    for (int i = 0; i < n; ++i) {
+        const int flags = ops[i].flags;
+        if (flags && !l && lanes_for_current_device(&l)) return 1;
+        if (flags & AIVC_OP_FORK) {
+            AIVC_CHECK_CUDA(cudaEventRecord(l->fork, main_s));
+            AIVC_CHECK_CUDA(cudaStreamWaitEvent(l->side, l->fork, 0));
+        }
+        if ((flags & AIVC_OP_JOIN) && side_dirty) {
+            AIVC_CHECK_CUDA(cudaEventRecord(l->join, l->side));
+            AIVC_CHECK_CUDA(cudaStreamWaitEvent(main_s, l->join, 0));
+            side_dirty = false;
+        }
+        const bool on_side = (flags & AIVC_OP_LANE1) != 0;
+        if (on_side) side_dirty = true;
+        if (aivc_conv2d_fused(ops + i, on_side ? (void *)l->side : stream)) {
             char tmp[400];
-            snprintf(tmp, sizeof(tmp), "%s", g_err);
+            snprintf(tmp, sizeof(tmp), "%.399s", g_err);
             AIVC_FAIL("stage %d/%d: %s", i, n, tmp);
         }
+    }
+    if (side_dirty) {                              // never leave work the caller cannot see
+        AIVC_CHECK_CUDA(cudaEventRecord(l->join, l->side));
+        AIVC_CHECK_CUDA(cudaStreamWaitEvent(main_s, l->join, 0));
+    }
     return 0;
 }
 

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_launch_dependents();
     stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
     stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
     if (p.gdn) stage_vec(sbeta, p.gdn_beta, N, 0.f, tid, NTHREADS);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait_prior_grid();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -251,7 +253,7 @@ int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, 
               size_t smem, cudaStream_t st) {
     AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          220 * 1024));
-    conv_tc_kernel<BK><<<grid, NTHREADS, smem, st>>>(a, b, g, p);
+    AIVC_CHECK_CUDA(launch_pdl(conv_tc_kernel<BK>, grid, dim3(NTHREADS), smem, st, a, b, g, p));
     AIVC_CHECK_LAUNCH("conv_tc_kernel");
     return 0;
 }
@@ -378,11 +380,11 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
     const int nctas = p.tiles_x * tiles_y * nphase;
     const size_t gam_bytes = gdn ? (size_t)cout * cout * 2 : 0;
     const size_t xsq_bytes = gdn ? (size_t)128 * cout * 2 : 0;
-    (void)nctas;
-    const size_t budget = 110 * 1024;               // always two CTAs per SM (also keeps the smem carve-out stable)
+    static const bool deep = getenv("AIVC_TC_DEEP") != nullptr;      // experiment switch
+    const size_t budget = (deep && nctas <= 148 * 3 / 2) ? 200 * 1024 : 110 * 1024;   // default: two CTAs per SM
     int nst = (int)((budget - 1024 - gam_bytes) / p.stage_bytes);
     if (nst > MAX_STAGES) nst = MAX_STAGES;
-    if (BK == 64 && nst > 3) nst = 3;               // measured: deeper 16 KB-stage rings only add L2 pressure
+    if (BK == 64 && nst > 3 && budget < 150 * 1024) nst = 3;   // measured: deeper 16 KB-stage rings only add L2 pressure
     if (nst < 2) nst = 2;
     p.nstages = nst;
     p.xsq_off = 0;                                   // x^2 tile aliases the stage ring ...

@@ -64,12 +64,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    pdl_launch_dependents();
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);          // weights/bias never depend on the prior grid
     stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait_prior_grid();                                    // activations / residuals below do
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -223,7 +225,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          220 * 1024));
     const int grid = ntiles < sm_count ? ntiles : sm_count;
-    conv3x3_tc_kernel<<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_kernel, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, p));
     AIVC_CHECK_LAUNCH("conv3x3_tc_kernel");
     return 0;
 }

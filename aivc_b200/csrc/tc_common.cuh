@@ -2,6 +2,7 @@
 // commit / ld, TMEM fences), UMMA descriptors, and the vectorised epilogue load/store.
 #pragma once
 #include <cuda.h>
+#include <utility>
 #include "common.cuh"
 
 namespace tcgen {
@@ -82,6 +83,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Programmatic dependent launch: let the next kernel's CTAs start their prologue while this grid
+// drains, and wait for the previous grid (and its memory) before touching dependent data.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -353,5 +358,19 @@ inline int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *di
     return 0;
 }
 
+
+// launch with the programmatic-stream-serialization attribute (PDL)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace tcgen

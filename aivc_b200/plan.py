@@ -37,13 +37,14 @@ class Config:
     tc_min_cin: int = 16           # tensor-core stages need cin % 16 == 0 and cout % 16 == 0
     hyper: str = 'auto'            # precision of h_a / h_s: 'fp32' (exact engine), 'bf16', or
                                    # 'auto' = same as `precision`
+    two_lanes: bool = True         # independent branches of attention blocks on two CUDA streams
 
     def key(self):
-        return (self.precision, self.tc_min_cin, self.hyper)
+        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes)
 
     def hyper_cfg(self):
         h = self.precision if self.hyper == 'auto' else self.hyper
-        return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h)
+        return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h, two_lanes=self.two_lanes)
 
 
 DEFAULT = Config()
@@ -105,6 +106,7 @@ class Stage:
     engine: int = ENGINE_SIMT
     cin_off: int = 0                # weight input channel 0 sits at this channel of the source pixel
     w_scale: float = 1.0            # folded into the packed weights (1/255 for level-unit inputs)
+    flags: int = 0                  # _lib.OP_LANE1 / OP_FORK / OP_JOIN
 
 
 class Graph:
@@ -212,9 +214,16 @@ def lower(m, x, g):
         _fold(g, res=x, post='leaky_relu')
         return y
     if n == 'SimplifiedAttention':
+        # trunk and attention paths are independent until the final gate: trunk runs on the side
+        # lane (second CUDA stream), the attention path on the caller's stream
+        i0 = len(g.stages)
         trunk = _lower_seq(m.trunk, x, g)
+        for s in g.stages[i0:]:
+            s.flags |= _lib.OP_LANE1
+        g.stages[i0].flags |= _lib.OP_FORK
         y = _lower_seq(m.attention, x, g)
         _fold(g, res=x, gate=trunk)
+        g.stages[-1].flags |= _lib.OP_JOIN
         return y
     if n == 'GDN':
         raise NotImplementedError('stand-alone GDN: wrap it with its producing conv')
@@ -329,8 +338,9 @@ class Plan:
         free, self.buffers = {}, []
         for i, s in enumerate(self.stages):
             t = s.dst
+            lane = s.flags & _lib.OP_LANE1
             if t.buf is None:
-                key = (t.h, t.w, t.c, t.pad, t.dtype)
+                key = (t.h, t.w, t.c, t.pad, t.dtype, lane)
                 pool = free.setdefault(key, [])
                 t.buf = pool.pop() if pool else Buffer(t.h, t.w, t.c, t.pad, t.dtype, self.device)
                 if t.buf not in self.buffers:
@@ -339,7 +349,9 @@ class Plan:
             for u in {id(x): x for x in (s.src, s.res, s.gate) if x is not None}.values():
                 if u.last == i and not u.external and u is not self.dst and u.buf is not None \
                         and u.c_off == 0 and u.c == u.buf.c:
-                    free.setdefault((u.h, u.w, u.c, u.pad, u.dtype), []).append(u.buf)
+                    # recycled only within the lane of the stage that read it last (streams of the
+                    # two lanes are ordered against each other only at fork / join)
+                    free.setdefault((u.h, u.w, u.c, u.pad, u.dtype, lane), []).append(u.buf)
 
     def _materialize(self):
         L = _lib.lib()
@@ -352,6 +364,7 @@ class Plan:
             op = self.ops[i]
             cin, cout = s.src.c, s.dst.c
             op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
+            op.flags = s.flags if self.cfg.two_lanes else 0
             op.inp, op.out = s.src.fmap(), s.dst.fmap()
             if s.kind == 2:
                 op.act = ACT[s.act]

@@ -88,8 +88,16 @@ typedef struct {
     const float *out_scale;    /* [cout] or NULL: GainMatrix 'enc' folded in (gain_matrix.py:122-124) */
     void *scratch;             /* SIMT GDN needs cout*h*w floats; else NULL */
     int32_t act_channels;      /* `act` applies to output channels [0, act_channels); 0 = all */
-    int32_t _r;
+    int32_t flags;             /* AIVC_OP_* : two-lane execution inside aivc_conv2d_fused_seq */
 } aivc_conv_op;
+
+/* Independent branches of a block (SimplifiedAttention's trunk and attention paths) run on two
+ * CUDA streams: lane 0 = the caller's stream, lane 1 = an internal side stream. */
+enum {
+    AIVC_OP_LANE1 = 1,   /* run this stage on the side stream */
+    AIVC_OP_FORK = 2,    /* before it: side stream waits for everything queued on the caller's stream */
+    AIVC_OP_JOIN = 4     /* before it: caller's stream waits for everything queued on the side stream */
+};
 
 /* ---- library ----------------------------------------------------------------------- */
 int aivc_abi_version(void);
