@@ -157,7 +157,7 @@ int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
     Lanes *l = nullptr;
     bool side_dirty = false;
     for (int i = 0; i < n; ++i) {
-        const int flags = ops[i].flags;
+        const int flags = g_prof_on ? 0 : ops[i].flags;   // per-stage timing needs kernels one at a time
         if (flags && !l && lanes_for_current_device(&l)) return 1;
         if (flags & AIVC_OP_FORK) {
             AIVC_CHECK_CUDA(cudaEventRecord(l->fork, main_s));

@@ -109,11 +109,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 for (int c = 0; c < chunks; ++c)
                     tma_load_2d(gam_tile + (size_t)c * N * p.kg * 2, &tmG, &bar_gamma, c * p.kg, 0);
             }
-            int it = 0;
+            int s = 0;
+            uint32_t par = 0;                                  // ring slot / phase, advanced incrementally
             for (int t = 0; t < ph.ntaps; ++t) {
-                for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                    const int s = it % NSTAGES;
-                    const uint32_t par = (uint32_t)((it / NSTAGES) & 1);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&bar_empty[s], par ^ 1u);
                     uint8_t *a_dst = tiles + (size_t)s * p.stage_bytes;
                     uint8_t *b_dst = a_dst + p.a_bytes;
@@ -124,6 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                         tma_load_5d(a_dst, &tmA, &bar_full[s], kc * BK, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
                                     my0 + ph.ay[t]);
                     tma_load_3d(b_dst, &tmB, &bar_full[s], kc * BK, 0, ph.widx[t]);
+                    if (++s == NSTAGES) { s = 0; par ^= 1u; }
                 }
             }
         }
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(N);
+            int s = 0;
+            uint32_t par = 0;
             for (int it = 0; it < total_it; ++it) {
-                const int s = it % NSTAGES;
-                const uint32_t par = (uint32_t)((it / NSTAGES) & 1);
                 mbar_wait(&bar_full[s], par);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(tiles + (size_t)s * p.stage_bytes);
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                     umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
                               (it > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(&bar_empty[s]);
+                if (++s == NSTAGES) { s = 0; par ^= 1u; }
             }
             umma_commit(&bar_acc);
             if (p.gdn) {

@@ -21,20 +21,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     const uint32_t addr = smem_u32(b);
+    if (mbar_try_wait(addr, parity)) return;                  // fast path: no clock reads
     const long long t0 = clock64();
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!done && clock64() - t0 > 4000000000LL) __trap();   // never hang the GPU
-    } while (!done);
+    while (!mbar_try_wait(addr, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();          // never hang the GPU
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
                                             int c1, int c2) {
@@ -182,7 +185,7 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
 // bias and scale are read from shared memory as broadcast float4.
 struct EpiCtx {
     FMap out, res, gate;
-    int post, act_channels;
+    int post, act_channels, dbg;
     bool has_scale, out_vec, res_vec, gate_vec;
 };
 
@@ -191,6 +194,7 @@ __device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, con
     EpiCtx c;
     c.out = out; c.res = res; c.gate = gate; c.post = post; c.act_channels = act_channels;
     c.has_scale = has_scale;
+    c.dbg = 0;
     c.out_vec = fmap_vec_ok(out);
     c.res_vec = res.data ? fmap_vec_ok(res) : false;
     c.gate_vec = gate.data ? fmap_vec_ok(gate) : false;
@@ -272,6 +276,7 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
             v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
         }
     }
+    if (c.dbg & 128) { if (v[0] == 123.456f) store16_at(c.out, out_elem + j0, v); return; }
     if (interior && c.out_vec) store16_at(c.out, out_elem + j0, v);
     else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
 }
@@ -285,7 +290,7 @@ __device__ __forceinline__ void res_fetch16(const EpiCtx &c, size_t res_elem, in
 
 template <int ACT>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
-                                        const EpiCtx &c, int oy, int ox, bool valid) {
+                                        const EpiCtx &c, int oy, int ox, bool valid, int c_begin = 0) {
     const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
     const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
     // bf16 residual rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
@@ -293,15 +298,18 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbia
     const bool pipe_res = valid && c.res.data && c.res_vec && c.res.dtype == AIVC_BF16;
     const size_t res_elem = pipe_res ? fm_index(c.res, oy, ox, 0) : 0;
     uint4 rb[2], rn[2];
-    if (pipe_res) res_fetch16(c, res_elem, 0, rn);
+    if (pipe_res) res_fetch16(c, res_elem, c_begin, rn);
 #pragma unroll 1
-    for (int j0 = 0; j0 < N; j0 += 16) {
+    for (int j0 = c_begin; j0 < N; j0 += 16) {
         if (pipe_res) {
             rb[0] = rn[0]; rb[1] = rn[1];
             if (j0 + 16 < N) res_fetch16(c, res_elem, j0 + 16, rn);
         }
         float v[16];
-        tmem_ld16(taddr + (uint32_t)j0, v);
+        if (c.dbg & 256) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (float)(j0 + i);
+        } else tmem_ld16(taddr + (uint32_t)j0, v);
         epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
         if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem, pipe_res ? rb : nullptr);
     }
@@ -309,13 +317,83 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbia
 
 __device__ __forceinline__ void epi_row_dispatch(int act, uint32_t taddr, int N, const float *sbias,
                                                  const float *sscale, const EpiCtx &c, int oy, int ox,
-                                                 bool valid) {
+                                                 bool valid, int c_begin = 0) {
+    // channels [c_begin, N)
     switch (act) {
-        case AIVC_ACT_LEAKY: epi_row<AIVC_ACT_LEAKY>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
-        case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
-        case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
-        default: epi_row<AIVC_ACT_NONE>(taddr, N, sbias, sscale, c, oy, ox, valid); break;
+        case AIVC_ACT_LEAKY: epi_row<AIVC_ACT_LEAKY>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        default: epi_row<AIVC_ACT_NONE>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
     }
+}
+
+// ---- staged epilogue: 32 channels of a row -> bf16 -> 64-byte row of a swizzled (64B mode) smem tile
+// that one thread then hands to a TMA store.  Everything up to the store is epi_tail16 without it.
+__device__ __forceinline__ void epi_values16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
+                                             int j0, bool valid) {
+    if (c.gate.data && valid) {
+        float g[16];
+        load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= g[i];
+    }
+    if (c.res.data && valid) {
+        float r[16];
+        load16(c.res, c.res_vec, oy, ox, j0, 16, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
+    }
+    if (c.post != AIVC_POST_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = post_apply(c.post, v[i]);
+    }
+    if (c.has_scale) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sscale + j0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 s = s4[q];
+            v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_row_staged32(uint32_t taddr, int ch0, const float *sbias, const float *sscale,
+                                                 const EpiCtx &c, int oy, int ox, bool valid, bool interior,
+                                                 uint8_t *stage, int row) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int j0 = ch0 + cc * 16;
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)j0, v);
+        epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
+        epi_values16(v, c, sscale, oy, ox, j0, valid);
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t off = (uint32_t)(row * 64 + cc * 32 + h * 16);
+            off ^= ((off >> 7) & 3u) << 4;                      // 64B swizzle, as the TMA store expects
+            *reinterpret_cast<uint4 *>(stage + off) = make_uint4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
+        }
+        if (valid && !interior) store16(c.out, c.out_vec, oy, ox, j0, 16, v);   // border replicas
+    }
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     (uint64_t)map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // bias / scale staged once per CTA in shared memory (zeros / ones when absent)
