@@ -44,7 +44,7 @@ struct TcParams {
     int mh, mw, out_step, mode;                  // mode 0: 3-D map, 1: 5-D map
     int tmem_cols, kg;                           // kg: columns per swizzle atom of the GDN operands
     int nstages, xsq_off;                        // pipeline depth; byte offset of the x^2 operand tile
-    uint32_t stage_bytes, a_bytes, b_bytes;
+    uint32_t stage_bytes, a_bytes, b_bytes, item_bytes;
     Phase ph[4];
 };
 
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                                                            const __grid_constant__ CUtensorMap tmG,
                                                            const TcParams p) {
     constexpr int ROWB = BK * 2;
+    constexpr int IPS = 64 / BK;                // (tap, chunk) items per pipeline stage
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc, bar_gamma, bar_xsq, bar_norm;
     __shared__ uint32_t tmem_slot;
@@ -109,22 +110,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 for (int c = 0; c < chunks; ++c)
                     tma_load_2d(gam_tile + (size_t)c * N * p.kg * 2, &tmG, &bar_gamma, c * p.kg, 0);
             }
-            int s = 0;
+            // A stage holds IPS = 64 / BK (tap, chunk) items, so it always carries four MMAs: with
+            // 16- or 32-channel chunks a per-item barrier round trip would cost more than its MMA
+            int s = 0, t = 0, kc = 0;
             uint32_t par = 0;                                  // ring slot / phase, advanced incrementally
-            for (int t = 0; t < ph.ntaps; ++t) {
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&bar_empty[s], par ^ 1u);
-                    uint8_t *a_dst = tiles + (size_t)s * p.stage_bytes;
-                    uint8_t *b_dst = a_dst + p.a_bytes;
-                    mbar_expect_tx(&bar_full[s], p.a_bytes + p.b_bytes);
+            for (int done = 0; done < total_it; done += IPS) {
+                const int n = min(IPS, total_it - done);
+                mbar_wait(&bar_empty[s], par ^ 1u);
+                mbar_expect_tx(&bar_full[s], (uint32_t)n * (p.a_bytes + p.b_bytes));
+                uint8_t *dst = tiles + (size_t)s * p.stage_bytes;
+                for (int g = 0; g < n; ++g, dst += p.item_bytes) {
                     if (p.mode == 0)
-                        tma_load_3d(a_dst, &tmA, &bar_full[s], kc * BK, mx0 + ph.ax[t], my0 + ph.ay[t]);
+                        tma_load_3d(dst, &tmA, &bar_full[s], kc * BK, mx0 + ph.ax[t], my0 + ph.ay[t]);
                     else
-                        tma_load_5d(a_dst, &tmA, &bar_full[s], kc * BK, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
+                        tma_load_5d(dst, &tmA, &bar_full[s], kc * BK, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
                                     my0 + ph.ay[t]);
-                    tma_load_3d(b_dst, &tmB, &bar_full[s], kc * BK, 0, ph.widx[t]);
-                    if (++s == NSTAGES) { s = 0; par ^= 1u; }
+                    tma_load_3d(dst + p.a_bytes, &tmB, &bar_full[s], kc * BK, 0, ph.widx[t]);
+                    if (++kc == p.kchunks) { kc = 0; ++t; }
                 }
+                if (++s == NSTAGES) { s = 0; par ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -133,16 +137,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
             const uint32_t idesc = make_idesc(N);
             int s = 0;
             uint32_t par = 0;
-            for (int it = 0; it < total_it; ++it) {
+            for (int done = 0; done < total_it; done += IPS) {
+                const int n = min(IPS, total_it - done);
                 mbar_wait(&bar_full[s], par);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(tiles + (size_t)s * p.stage_bytes);
-                const uint64_t adesc = make_desc(a_addr, ROWB);
-                const uint64_t bdesc = make_desc(a_addr + p.a_bytes, ROWB);
+                uint32_t a_addr = smem_u32(tiles + (size_t)s * p.stage_bytes);
+                for (int g = 0; g < n; ++g, a_addr += p.item_bytes) {
+                    const uint64_t adesc = make_desc(a_addr, ROWB);
+                    const uint64_t bdesc = make_desc(a_addr + p.a_bytes, ROWB);
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; ++kk)
-                    umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                              (it > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < BK / 16; ++kk)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                  (done > 0 || g > 0 || kk > 0) ? 1u : 0u);
+                }
                 umma_commit(&bar_empty[s]);
                 if (++s == NSTAGES) { s = 0; par ^= 1u; }
             }
@@ -295,7 +302,8 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
     while (p.tmem_cols < need_cols) p.tmem_cols <<= 1;
     p.a_bytes = 128u * rowb;
     p.b_bytes = (uint32_t)cout * rowb;
-    p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+    p.item_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+    p.stage_bytes = p.item_bytes * (uint32_t)(64 / BK);
 
     const aivc_fmap &in = op->in;
     const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
