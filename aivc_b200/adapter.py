@@ -1,0 +1,138 @@
+"""Reference-facing entry points on top of FrameCodec.
+
+``gop_forward(model, model_input)`` implements the contract of the (missing) upstream
+``models.FullNet.GOP_forward`` as read off its callers:
+  input  : model_management.py:307-317  (GOP_struct, GOP_struct_name, raw_frames, idx_rate,
+           index_GOP_in_video, generate_bitstream, real_idx_first_frame, bitstream_dir,
+           flag_bitstream_debug)
+  output : net_out['frame_i'] with x_hat (YUV420 dict), alpha, beta, warping, code and the four
+           rate tensors consumed by loss_function.py:158-204
+  files  : with generate_bitstream it leaves '<bitstream_dir>/<idx_gop>g' (what cat_one_gop,
+           cat_binary_files.py:19-101, would have produced) and 'data_dim.pkl' (header.py:175-177),
+           so the reference's cat_one_video (model_management.py:216-223) finishes the job.
+
+``decode_video(model, video_bytes)`` is decode_one_video (real_life/decode.py:44-154) without
+the temp-dir round trips: bytes in, decoded uint8 planes out.
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import container
+from .codec import FrameCodec, latent_dims
+from .gop import generate_gop_struct, FRAME_I
+from .plan import Config
+
+_CODECS = {}
+
+
+def codec_for(model, h, w, device, cfg=None, idx_rate=0.):
+    cfg = cfg or Config()
+    key = (id(model), h, w, str(device), cfg.key(), float(idx_rate))
+    c = _CODECS.get(key)
+    if c is None:
+        c = _CODECS[key] = FrameCodec(model, h, w, device, cfg, idx_rate)
+    return c
+
+
+def _to_planes(yuv, device):
+    """{'y','u','v'} fp32 [1,1,H,W] in [0,1] (any device) -> flat uint8 device planes."""
+    return tuple((yuv[k].to(device).float().clamp(0, 1) * 255.).round().to(torch.uint8).reshape(-1).contiguous()
+                 for k in 'yuv')
+
+
+def _to_yuv(planes, h, w):
+    hc, wc = (h + 1) // 2, (w + 1) // 2
+    y, u, v = planes
+    return {'y': y.view(1, 1, h, w).float() / 255., 'u': u.view(1, 1, hc, wc).float() / 255.,
+            'v': v.view(1, 1, hc, wc).float() / 255.}
+
+
+def _section_bits(frame_bytes):
+    """Real coded size of the four sections of a frame, in bits (length prefixes excluded)."""
+    bits, pos = [], 0
+    for _ in range(4):
+        n = int.from_bytes(frame_bytes[pos:pos + 4], 'big')
+        bits.append(8.0 * n)
+        pos += 4 + n
+    return bits
+
+
+def gop_forward(model, model_input, device=None, cfg=None):
+    gop = model_input['GOP_struct']
+    name = model_input.get('GOP_struct_name') or ''
+    raw = model_input['raw_frames']
+    idx_rate = float(model_input.get('idx_rate', 0.) or 0.)
+    first = raw['frame_0']['y']
+    h, w = first.shape[2:]
+    if device is None:
+        device = first.device if first.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    codec = codec_for(model, h, w, device, cfg, idx_rate)
+    frames = {f: _to_planes(raw[f], device) for f in gop}
+    bts, rec = codec.encode_gop(frames, gop)
+
+    net_out = {}
+    in_layer = model.in_layer
+    for f in gop:
+        mz, my, cz, cy = _section_bits(bts[f])
+        x_hat = _to_yuv(rec[f], h, w)
+        code = in_layer({k: (frames[f][i].view(1, 1, *x_hat[k].shape[2:]).float() / 255.)
+                         for i, k in enumerate('yuv')})
+        is_i = gop[f]['type'] == FRAME_I
+        one = torch.ones((1, 3, h, w), device=device)
+        net_out[f] = {
+            'x_hat': x_hat, 'code': code,
+            # the fused pipeline does not materialise alpha / beta / the warped prediction; the
+            # values below are the I-frame constants (decode.py:500-504) -- they only feed logging
+            'alpha': one, 'beta': one, 'warping': code if is_i else in_layer(x_hat),
+            'mode_rate_y': torch.tensor([my], device=device), 'mode_rate_z': torch.tensor([mz], device=device),
+            'codec_rate_y': torch.tensor([cy], device=device), 'codec_rate_z': torch.tensor([cz], device=device),
+        }
+
+    if model_input.get('generate_bitstream'):
+        d = model_input.get('bitstream_dir') or './'
+        if not d.endswith('/'):
+            d += '/'
+        os.makedirs(d, exist_ok=True)
+        order = sorted(gop, key=lambda f: int(f.split('_')[1]))
+        idx_gop = int(model_input.get('index_GOP_in_video', 0) or 0)
+        with open(d + str(idx_gop) + 'g', 'wb') as fo:
+            fo.write(container.pack_gop(name, [bts[f] for f in order], idx_rate))
+        dims_y, dims_z = latent_dims(h, w)
+        with open(d + 'data_dim.pkl', 'wb') as fo:
+            pickle.dump({'x': (h, w), 'y': dims_y, 'z': dims_z}, fo, pickle.HIGHEST_PROTOCOL)
+    return net_out
+
+
+def encode_video(model, gops_of_frames, gop_name, h, w, device='cuda:0', cfg=None, idx_rate=0., idx_first=0):
+    """gops_of_frames: list (one per GOP) of {'frame_i': (y,u,v) uint8 device planes}.
+    Returns the complete .bin byte string (same layout as cat_one_video writes)."""
+    gop = generate_gop_struct(gop_name)
+    order = sorted(gop, key=lambda f: int(f.split('_')[1]))
+    codec = codec_for(model, h, w, torch.device(device), cfg, idx_rate)
+    packed = []
+    for frames in gops_of_frames:
+        bts, _ = codec.encode_gop(frames, gop)
+        packed.append(container.pack_gop(gop_name, [bts[f] for f in order], idx_rate))
+    dims_y, dims_z = latent_dims(h, w)
+    n = len(order) * len(gops_of_frames)
+    return container.pack_video((h, w), dims_y, dims_z, packed, idx_first, idx_first + n - 1)
+
+
+def decode_video(model, video_bytes, device='cuda:0', cfg=None):
+    """-> (list over GOPs of {'frame_i': (y,u,v) uint8 device planes}, data_dim, idx_first, idx_last)"""
+    dims, gops, first, last = container.unpack_video(video_bytes)
+    h, w = dims['x']
+    out = []
+    for g in gops:
+        name, idx_rate, frames = container.unpack_gop(g)
+        gop = generate_gop_struct(name)
+        order = sorted(gop, key=lambda f: int(f.split('_')[1]))
+        if len(order) != len(frames):
+            raise ValueError('GOP %s announces %d frames, bitstream holds %d' % (name, len(order), len(frames)))
+        codec = codec_for(model, h, w, torch.device(device), cfg, idx_rate)
+        out.append(codec.decode_gop(dict(zip(order, frames)), gop))
+    return out, dims, first, last

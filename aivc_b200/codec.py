@@ -396,4 +396,5 @@ def planes_to_device(yuv_u8, device):
 
 
 def gop_forward(model, model_input):
-    raise NotImplementedError('FullNet.GOP_forward adapter: see aivc_b200.adapter')
+    from .adapter import gop_forward as _gf
+    return _gf(model, model_input)

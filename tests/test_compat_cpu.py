@@ -107,6 +107,52 @@ dist.destroy_process_group()
 '''
 
 
+_WORKER2 = r'''
+import os, sys, hashlib
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from aivc_b200 import sharding, gop as G
+dist.init_process_group('gloo')
+r, n = dist.get_rank(), dist.get_world_size()
+class FakeCodec:
+    """Deterministic stand-in: the 'reconstruction' mixes the frame with its references, so a
+    wrong or missing reference exchange changes every later frame."""
+    def encode_frame(self, planes, t, prev, nxt):
+        rec = tuple((p.to(torch.int32) * 3 + (0 if prev is None else prev[i].to(torch.int32))
+                     + 2 * (0 if nxt is None else nxt[i].to(torch.int32)) + t).remainder(251).to(torch.uint8)
+                    for i, p in enumerate(planes))
+        return hashlib.md5(b''.join(x.numpy().tobytes() for x in rec)).digest(), rec
+    def decode_frame(self, b, t, prev, nxt):
+        return self.store[b]
+gop = G.generate_gop_struct('1_GOP_8')
+g = torch.Generator().manual_seed(0)
+sizes = [48, 12, 12]
+frames = {f: tuple(torch.randint(0, 256, (s,), dtype=torch.uint8, generator=g) for s in sizes) for f in sorted(gop)}
+codec = FakeCodec()
+bts, rec = sharding.encode_gop_frame_parallel(codec, frames, gop, sizes, 'cpu')
+# serial reference on every rank
+ref = {}
+for f in G.coding_order(gop):
+    e = gop[f]
+    _, ref[f] = codec.encode_frame(frames[f], e['type'], ref.get(e['prev_ref']), ref.get(e['next_ref']))
+assert all(all(torch.equal(a, b) for a, b in zip(rec[f], ref[f])) for f in gop)
+if r == 0:
+    assert sorted(bts) == sorted(gop)
+    print('OK levels', [len(l) for l in G.levels(gop)])
+dist.destroy_process_group()
+'''
+
+
+def test_frame_level_sharding_two_ranks_gloo(tmp_path):
+    script = tmp_path / 'w2.py'
+    script.write_text(_WORKER2 % ROOT)
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29543', str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'OK levels [1, 1, 1, 2, 4]' in out.stdout
+
+
 def test_gop_sharding_two_ranks_gloo(tmp_path):
     script = tmp_path / 'w.py'
     script.write_text(_WORKER % ROOT)

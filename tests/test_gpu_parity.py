@@ -210,3 +210,42 @@ def test_closed_loop_odd_and_reference_sizes(size, dev):
         assert len(bts[f]) > 16
         for a, b in zip(rec[f], dec[f]):
             assert torch.equal(a, b)
+
+
+def test_gop_forward_contract_and_video_roundtrip(golden_dir, dev, tmp_path):
+    """FullNet.GOP_forward with the reference's model_input dict (model_management.py:307-317):
+    net_out keys, the GOP file it leaves behind, and decode_video of the assembled .bin."""
+    from aivc_b200 import models, gop as G, container, adapter
+    from aivc_b200.plan import Config
+    fx = np.load(os.path.join(golden_dir, 'system_80x112.npz'))
+    h, w = int(fx['H']), int(fx['W'])
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    gop = G.generate_gop_struct('1_GOP_2')
+    raw = {}
+    for t in range(3):
+        raw['frame_%d' % t] = {k: torch.from_numpy(fx['src_frame_%d_%s' % (t, k)].astype(np.float32) / 255.)[None, None].to(dev)
+                               for k in 'yuv'}
+    d = str(tmp_path) + '/bs/'
+    model_input = {'GOP_struct': gop, 'GOP_struct_name': '1_GOP_2', 'raw_frames': raw, 'idx_rate': 0.,
+                   'index_GOP_in_video': 0, 'generate_bitstream': True, 'real_idx_first_frame': 0,
+                   'bitstream_dir': d, 'flag_bitstream_debug': False}
+    out = adapter.gop_forward(net, model_input, cfg=Config(precision='fp32'))
+    for f in gop:
+        for key in ('x_hat', 'alpha', 'beta', 'warping', 'code', 'mode_rate_y', 'mode_rate_z', 'codec_rate_y',
+                    'codec_rate_z'):
+            assert key in out[f], key
+        for k in 'yuv':
+            got = (out[f]['x_hat'][k].cpu().numpy() * 255).round().astype(np.uint8).reshape(-1)
+            assert np.array_equal(got, fx['spec_rec_%s_%s' % (f, k)].reshape(-1))     # fp32 engine == oracle
+    gbytes = open(d + '0g', 'rb').read()
+    name, rate, frames = container.unpack_gop(gbytes)
+    assert name == '1_GOP_2' and [bytes(b) for b in frames] == [fx['spec_bytes_frame_%d' % i].tobytes() for i in range(3)]
+    # the same content through the video container and back
+    from aivc_b200.codec import latent_dims
+    dy, dz = latent_dims(h, w)
+    video = container.pack_video((h, w), dy, dz, [gbytes], 0, 2)
+    dec, dims, first, last = adapter.decode_video(net, video, dev, Config(precision='fp32'))
+    assert dims['x'] == (h, w) and (first, last) == (0, 2)
+    for f in gop:
+        for k, p in zip('yuv', dec[0][f]):
+            assert np.array_equal(p.cpu().numpy(), fx['spec_rec_%s_%s' % (f, k)].reshape(-1))
