@@ -223,8 +223,10 @@ def test_gop_forward_contract_and_video_roundtrip(golden_dir, dev, tmp_path):
     gop = G.generate_gop_struct('1_GOP_2')
     raw = {}
     for t in range(3):
-        raw['frame_%d' % t] = {k: torch.from_numpy(fx['src_frame_%d_%s' % (t, k)].astype(np.float32) / 255.)[None, None].to(dev)
-                               for k in 'yuv'}
+        raw['frame_%d' % t] = {}
+        for k in 'yuv':
+            a = fx['src_frame_%d_%s' % (t, k)].astype(np.float32) / 255.
+            raw['frame_%d' % t][k] = torch.from_numpy(a).reshape(1, 1, *a.shape[-2:]).to(dev)
     d = str(tmp_path) + '/bs/'
     model_input = {'GOP_struct': gop, 'GOP_struct_name': '1_GOP_2', 'raw_frames': raw, 'idx_rate': 0.,
                    'index_GOP_in_video': 0, 'generate_bitstream': True, 'real_idx_first_frame': 0,
