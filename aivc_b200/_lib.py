@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libaivc_b200.so')
+# AIVC_B200_LIB: alternative build of the same ABI (A/B timing of kernel changes on one box)
+LIB_PATH = os.environ.get('AIVC_B200_LIB') or os.path.join(_HERE, 'libaivc_b200.so')
 
 F32, BF16 = 0, 1
 ACT = {'no': 0, 'none': 0, 'leaky_relu': 1, 'relu': 2, 'sigmoid': 3, 'gdn': 4, 'gdn_inverse': 5}

@@ -24,15 +24,25 @@ using namespace tcgen;
 
 namespace {
 
-constexpr int NTHREADS = 576;       // TMA warp, MMA warp, 16 epilogue warps: 4 teams = (sub-tile j, channel half h) x 4 lane quarters
+// SUB = 128-row accumulators (sub-tiles) per CTA tile.  SUB = 2: 32 x 8 pixel tiles, 18 warps, one CTA per
+// SM (large layers).  SUB = 1: 16 x 8 pixel tiles, 10 warps, <= 112 KB of shared memory and 256 TMEM
+// columns so that TWO CTAs share an SM, optionally with the output channels split over two work items
+// (small layers: 68 x 120 latents give 75 tiles -> 150 work items for 148 SMs).
 // The warp scheduler favours HIGHER warp ids, so the two latency-critical single-thread roles get the
 // highest ids and are never starved by the ALU-heavy epilogue warps of their sub-partition.
-constexpr int TMA_WARP = 16, MMA_WARP = 17;
+template <int SUB>
+struct Cfg {
+    static constexpr int EPI_WARPS = 8 * SUB;               // teams = (sub-tile j, channel half h) x 4 lane quarters
+    static constexpr int NTHREADS = 32 * (EPI_WARPS + 2);
+    static constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+    static constexpr int TILE_H = 16 * SUB;
+    static constexpr uint32_t PATCH_BYTES = (TILE_H + 2) * 10 * 128;          // per 64-channel chunk
+    static constexpr uint32_t A_SLOT = (PATCH_BYTES + 1023) & ~1023u;
+    static constexpr uint32_t TMEM_COLS = 256 * SUB;          // two accumulator buffers of SUB x 128 columns
+};
 constexpr int STAGE_BYTES = 128 * 64;   // one team's store staging tile: 128 rows x 32 channels bf16
-constexpr int TILE_H = 32, TILE_W = 8;
+constexpr int TILE_W = 8;
 constexpr int PATCH_W = TILE_W + 2;                                             // 10 pixels
-constexpr uint32_t PATCH_BYTES = (TILE_H + 2) * PATCH_W * 128;                   // 43520 B per 64-channel chunk
-constexpr uint32_t A_SLOT = (PATCH_BYTES + 1023) & ~1023u;                       // 44032 B
 constexpr int NA = 2;               // activation patches in flight
 constexpr int NG_MAX = 4;           // weight groups (3 taps = one kernel row) in flight
 
@@ -40,56 +50,161 @@ struct Tc3Params {
     FMap out, res, gate;
     const float *bias, *out_scale;
     int cout, kchunks;
-    int act, post, act_channels;
-    int tiles_x, ntiles;
+    int ncta, nsplit;                 // output channels per work item; work items per pixel tile
+    int act, post;
+    int tiles_x, nitems;
     int in_pad;
-    uint32_t b_bytes, b_slot;         // one tap's weight slice (cout x 64 ch) and its 1 KB-rounded slot
+    uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
-    int tma_store;                    // epilogue stores through smem + TMA (bf16, 64-channel multiples)
+    int tma_store;                    // epilogue stores through smem + TMA (bf16, 32-channel multiples)
     int dbg;                          // AIVC_TC3_DBG bits: timing experiments only (wrong results)
 };
 
-template <int ACT>
+// 16 channels of this thread's pixel as packed bf16 (two 16-byte loads)
+__device__ __forceinline__ void ldg_bf16x16(const __nv_bfloat16 *ptr, uint4 &r0, uint4 &r1) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(ptr);
+    r0 = q[0];
+    r1 = q[1];
+}
+__device__ __forceinline__ void add_bf16x16(float *v, const uint4 &r0, const uint4 &r1) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint4 &r = h ? r1 : r0;
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[8 * h + 2 * q] += __uint_as_float(w[q] << 16);
+            v[8 * h + 2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        }
+    }
+}
+
+// border replicas of an edge pixel (rare: edge tiles only), kept out of line so that its addressing
+// does not cost the hot path registers
+__device__ __noinline__ void border_store_bf16x16(const Tc3Params *p, int ch, int oy, int ox, uint4 lo, uint4 hi) {
+    const FMap &m = p->out;
+    const int pd = m.pad;
+    const int y0 = (oy == 0) ? 0 : oy + pd, y1 = (oy == m.h - 1) ? oy + 2 * pd : oy + pd;
+    const int x0 = (ox == 0) ? 0 : ox + pd, x1 = (ox == m.w - 1) ? ox + 2 * pd : ox + pd;
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+            if (yy == oy + pd && xx == ox + pd) continue;       // the pixel itself goes out with the TMA store
+            uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride +
+                                                 m.c_off + ch);
+            q[0] = lo;
+            q[1] = hi;
+        }
+}
+
+// One 32-channel chunk of an accumulator row -> bias, activation, residual, post, scale -> bf16 ->
+// 64-byte row of the team's swizzled (64B mode) staging tile.  `rc`: residual of the chunk, already in
+// registers `rr` (prefetched while the tensor pipe was still working on this tile).
+template <int ACT, bool USE_RES>
+__device__ __forceinline__ void chunk32_to_stage(const Tc3Params &p, uint32_t taddr, int ch0, int n0,
+                                                 const float *sbias, const float *sscale, uint4 (&rr)[4],
+                                                 const __nv_bfloat16 *res_next, int oy, int ox, bool edge,
+                                                 uint8_t *stage, int row) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int j0 = ch0 + cc * 16;
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)j0, v);
+        epi_bias_act16<ACT>(v, sbias, n0 + j0, 0);
+        if (USE_RES) {
+            add_bf16x16(v, rr[2 * cc], rr[2 * cc + 1]);
+            // the registers just consumed take the same 16 channels of the team's NEXT 32-channel chunk
+            if (res_next) ldg_bf16x16(res_next + cc * 16, rr[2 * cc], rr[2 * cc + 1]);
+        }
+        post_apply16(p.post, v);
+        if (p.out_scale) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(sscale + n0 + j0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 sc = s4[q];
+                v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+            }
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+        }
+        const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
+        uint32_t off = (uint32_t)(row * 64 + cc * 32);
+        off ^= ((off >> 7) & 3u) << 4;                          // 64B swizzle, as the TMA store expects
+        *reinterpret_cast<uint4 *>(stage + off) = lo;
+        *reinterpret_cast<uint4 *>(stage + (off ^ 16u)) = hi;
+        if (edge) border_store_bf16x16(&p, n0 + j0, oy, ox, lo, hi);
+    }
+}
+
+template <int SUB, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
                                               const float *sbias, const float *sscale, uint64_t *acc_full,
                                               uint64_t *acc_empty, uint32_t tmem_base, int warp, int lane) {
+    constexpr int TILE_H = Cfg<SUB>::TILE_H;
     const int quarter = warp & 3, team = warp >> 2, j = team >> 1, h = team & 1;
     const int row = quarter * 32 + lane;
     const bool leader = ((warp & 3) == 0) && lane == 0;
-    const int N = p.cout;
-    const int c_lo = h * 64, c_hi = min(N, c_lo + 64);
-    EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, p.act_channels, p.out_scale != nullptr);
-    ctx.dbg = p.dbg;
+    const int N = p.ncta;
+    const int half = (N == 64) ? 32 : 64;                   // channels per team
+    const int c_lo = h * half, c_hi = min(N, c_lo + half);
+    // bf16 residuals with 16-byte aligned channel groups are prefetched into registers one 32-channel
+    // chunk ahead -- the first chunk before the accumulator is even complete -- so their L2 latency
+    // (about 1 us under load) never sits on the epilogue's critical path
+    // (RES kernels are only launched with TMA stores and a residual the host found prefetchable)
+    constexpr bool res_fast = RES;
+    EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr);
     uint8_t *my_stage = stage + team * STAGE_BYTES;
     uint32_t it = 0;
     bool store_pending = false;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
         const uint32_t buf = it & 1u;
+        const int tile = item / p.nsplit, n0 = (item - tile * p.nsplit) * N;
         const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
         const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
         const bool valid = (oy < p.out.h) && (ox < p.out.w);
+        const bool use_res = res_fast && valid;
+        ctx.out.c_off = p.out.c_off + n0;
+        const __nv_bfloat16 *res_px = use_res ? (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0) : nullptr;
+        uint4 rr[4];
+        if (res_fast) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (use_res && c_lo < N) {                              // first 32 channels: issued before the wait
+            ldg_bf16x16(res_px + c_lo, rr[0], rr[1]);
+            ldg_bf16x16(res_px + c_lo + 16, rr[2], rr[3]);
+        }
         mbar_wait(&acc_full[buf], (it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256u + (uint32_t)(j * 128);
+        const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(128 * SUB) + (uint32_t)(j * 128);
         if (c_lo < N && !(p.dbg & 2)) {
             if (p.tma_store) {
-                const bool interior = ctx.out.pad == 0 || (oy > 0 && oy < p.out.h - 1 && ox > 0 && ox < p.out.w - 1);
+                const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
                 for (int ch0 = c_lo; ch0 < c_hi; ch0 += 32) {
                     if (store_pending) {                       // staging tile still being read by the last store?
                         if (leader) tma_store_wait_read();
                         named_bar_sync(1 + team, 128);
                     }
-                    epi_row_staged32<ACT>(tl, ch0, sbias, sscale, ctx, oy, ox, valid, interior, my_stage, row);
+                    // (warp-uniform choice: tcgen05.ld inside is .sync.aligned; rows outside the image add zeros)
+                    if (RES)
+                        chunk32_to_stage<ACT, true>(p, tl, ch0, n0, sbias, sscale, rr,
+                                                    (use_res && ch0 + 32 < c_hi) ? res_px + ch0 + 32 : nullptr, oy, ox, edge, my_stage, row);
+                    else
+                        epi_row_staged32<ACT>(tl, ch0, sbias + n0, sscale + n0, ctx, oy, ox, valid, !edge, my_stage, row);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     named_bar_sync(1 + team, 128);
                     if (leader) {
-                        tma_store_3d(tmO, my_stage, ch0, x0, y0 + 16 * j);
+                        tma_store_3d(tmO, my_stage, n0 + ch0, x0, y0 + 16 * j);
                         tma_store_commit();
                     }
                     store_pending = true;
                 }
             } else {
-                epi_row<ACT>(tl, c_hi, sbias, sscale, ctx, oy, ox, valid, c_lo);
+                ctx.res.c_off = p.res.c_off + n0; ctx.gate.c_off = p.gate.c_off + n0;
+                epi_row<ACT>(tl, c_hi, sbias + n0, sscale + n0, ctx, oy, ox, valid, c_lo);
             }
         }
         tc_fence_before();
@@ -98,10 +213,13 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
     if (store_pending && leader) tma_store_wait_read();        // smem must outlive the last store's read
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                 const __grid_constant__ CUtensorMap tmO,
-                                                                 const Tc3Params p) {
+template <int SUB, bool RES>
+__global__ void __launch_bounds__(Cfg<SUB>::NTHREADS, SUB == 1 ? 2 : 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
+    using K = Cfg<SUB>;
+    constexpr int NTHREADS = K::NTHREADS, TILE_H = K::TILE_H;
+    constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[NA], a_empty[NA], g_full[NG_MAX], g_empty[NG_MAX], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
@@ -110,40 +228,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
     uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *g_ring = a_ring + NA * A_SLOT;
     const uint32_t g_slot = 3u * p.b_slot;
-    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB
+    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // TEAMS x 8 KB
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = p.cout;
+    const int N = p.ncta;
 
     if (tid == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NG_MAX; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 512); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 32 * K::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) {
+    if (warp == K::MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&tmem_slot)),
-                     "r"(512)
+                     "r"(K::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_launch_dependents();
-    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);          // weights/bias never depend on the prior grid
-    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
+    stage_vec(sbias, p.bias, p.cout, 0.f, tid, NTHREADS);     // weights/bias never depend on the prior grid
+    stage_vec(sscale, p.out_scale, p.cout, 1.f, tid, NTHREADS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     pdl_wait_prior_grid();                                    // activations / residuals below do
 
-    if (warp == TMA_WARP) {
+    if (warp == K::TMA_WARP) {
         // ===================== TMA producer =====================
-        // per tile and 64-channel chunk: ONE activation patch (34 x 10 pixels) that serves all nine
-        // taps, and three weight groups (one kernel row = 3 taps each), every group on one barrier
+        // per work item and 64-channel chunk: ONE activation patch ((TILE_H+2) x 10 pixels) that serves
+        // all nine taps, and three weight groups (one kernel row = 3 taps each), every group on one barrier
         if (lane == 0) {
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0;          // ring slot / phase, advanced incrementally
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+                const int tile = item / p.nsplit, n0 = (item - tile * p.nsplit) * N;
                 const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&a_empty[sa], pa ^ 1u);
@@ -162,28 +281,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                             uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx)
-                                tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], kc * 64, 0, ky * 3 + kx);
+                                tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], kc * 64, n0, ky * 3 + kx);
                         }
                         if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                     }
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == K::MMA_WARP) {
         // ===================== MMA issuer =====================
-        // 24 MMAs (3 taps x 2 sub-tiles x 4 k-steps) per barrier wait: the issuing thread's
-        // bookkeeping must stay well below the 1536 tensor cycles they take
+        // 12 SUB MMAs (3 taps x SUB sub-tiles x 4 k-steps) per barrier wait: the issuing thread's
+        // bookkeeping must stay well below the tensor cycles they take
         if (lane == 0) {
             const uint32_t idesc = make_idesc(N);
             // descriptor template: K-major, 128B swizzle, 8-row groups PATCH_W rows apart (the
             // swizzle is a function of the absolute smem address, so any 128 B-aligned start works)
             const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
                 const uint32_t buf = it & 1u;
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t acc = tmem_base + buf * 256u;
+                const uint32_t acc = tmem_base + buf * (uint32_t)(128 * SUB);
                 uint32_t accum = 0;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&a_full[sa], pa);
@@ -197,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
                             for (int kx = 0; kx < 3; ++kx) {
                                 const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
 #pragma unroll
-                                for (int j = 0; j < 2; ++j) {
+                                for (int j = 0; j < SUB; ++j) {
                                     const uint32_t start = a_addr + (uint32_t)((ky + 16 * j) * PATCH_W + kx) * 128u;
                                     const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
 #pragma unroll
@@ -219,22 +338,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3x3_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ===================== epilogue (warps 0..15) =====================
+        // ===================== epilogue (warps 0 .. 8 SUB - 1) =====================
         switch (p.act) {
-            case AIVC_ACT_LEAKY: epilogue_team<AIVC_ACT_LEAKY>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_RELU: epilogue_team<AIVC_ACT_RELU>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_SIGMOID: epilogue_team<AIVC_ACT_SIGMOID>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            default: epilogue_team<AIVC_ACT_NONE>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_LEAKY: epilogue_team<SUB, AIVC_ACT_LEAKY, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_RELU: epilogue_team<SUB, AIVC_ACT_RELU, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_SIGMOID: epilogue_team<SUB, AIVC_ACT_SIGMOID, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
+            default: epilogue_team<SUB, AIVC_ACT_NONE, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) {
+    if (warp == K::MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS)
                      : "memory");
     }
+}
+
+template <int SUB, bool RES>
+int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const Tc3Params &p, int grid,
+               size_t smem, cudaStream_t st) {
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<SUB, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SUB == 1 ? 166 * 1024 : 220 * 1024));
+    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_kernel<SUB, RES>, dim3(grid), dim3(Cfg<SUB>::NTHREADS), smem, st, a, b, o, p));
+    AIVC_CHECK_LAUNCH("conv3x3_tc_kernel");
+    return 0;
 }
 
 }  // namespace
@@ -246,9 +375,17 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (cin % 64 || cout % 16 || cout > 128) return -1;
     if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN) return -1;
     if (op->in.dtype != AIVC_BF16 || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 8) return -1;
-    const int tiles_x = ceil_div(op->out.w, TILE_W), tiles_y = ceil_div(op->out.h, TILE_H);
-    const int ntiles = tiles_x * tiles_y;
-    if (ntiles < 296) return -1;            // < 2 tiles per SM: the 128-pixel-tile kernel fills the chip better
+    if (op->act_channels) return -1;
+    static const int force_sub = getenv("AIVC_TC3_SUB") ? atoi(getenv("AIVC_TC3_SUB")) : 0;   // experiment switch
+    const int tiles_x = ceil_div(op->out.w, TILE_W);
+    // big layers: 32-row tiles, one CTA per SM.  Fewer than two of those per SM: 16-row tiles, two CTAs
+    // per SM and (wide layers) the output channels of a tile split over two work items.
+    const int tiles32 = tiles_x * ceil_div(op->out.h, 32);
+    int sub = tiles32 >= 296 ? 2 : 1;
+    if (force_sub == 1 || force_sub == 2) sub = force_sub;
+    else if (tiles32 >= 148 && tiles32 < 296) return -1;   // one-and-a-bit waves either way: the 128-pixel-tile kernel fills the chip better
+    const int tile_h = 16 * sub;
+    const int ntiles = tiles_x * ceil_div(op->out.h, tile_h);
 
     Tc3Params p;
     memset(&p, 0, sizeof(p));
@@ -257,13 +394,21 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->gate.data) p.gate = to_dev(op->gate);
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / 64;
-    p.act = op->act; p.post = op->post; p.act_channels = op->act_channels;
-    p.tiles_x = tiles_x; p.ntiles = ntiles; p.in_pad = op->in.pad;
-    p.b_bytes = (uint32_t)cout * 128u;
+    p.nsplit = (sub == 1 && cout == 128 && ntiles < 296) ? 2 : 1;
+    p.ncta = cout / p.nsplit;
+    p.act = op->act; p.post = op->post;
+    p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.in_pad = op->in.pad;
+    p.b_bytes = (uint32_t)p.ncta * 128u;
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
+    const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
+    const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES;
+    // SUB = 1 aims at two CTAs per SM (<= 111 KB each) when two weight groups fit in that
+    const size_t two_cta = 111 * 1024;
+    const bool pair = sub == 1 && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
+    const size_t budget = sub == 2 ? 219 * 1024 : (pair ? two_cta : 165 * 1024);
     p.ng = NG_MAX;
-    while (1024 + (size_t)NA * A_SLOT + (size_t)p.ng * 3 * p.b_slot + 4 * STAGE_BYTES > 219 * 1024 && p.ng > 1) --p.ng;
+    while (fixed + (size_t)p.ng * 3 * p.b_slot > budget && p.ng > 1) --p.ng;
     if (p.ng < 2) return -1;
 
     const aivc_fmap &in = op->in;
@@ -272,19 +417,25 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
         cuuint64_t strides[2] = {pix_b, row_b};
-        cuuint32_t box[3] = {64, PATCH_W, TILE_H + 2};
+        cuuint32_t box[3] = {64, PATCH_W, (cuuint32_t)(tile_h + 2)};
         if (encode_map(&tmA, (char *)in.data + (size_t)in.c_off * 2, 3, dims, strides, box, 128, "A/3x3")) return 1;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)cout, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.ncta, 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, 128, "B/3x3")) return 1;
     }
     CUtensorMap tmO;
     memset(&tmO, 0, sizeof(tmO));
     const aivc_fmap &o = op->out;
-    p.tma_store = (o.dtype == AIVC_BF16 && o.c_off % 8 == 0 && o.c_stride % 8 == 0 && cout % 32 == 0 &&
+    // staged epilogue (smem + TMA store, residual prefetched into registers): bf16 output in 32-channel
+    // multiples, no gate, residual (if any) bf16 with 16-byte aligned channel groups
+    const aivc_fmap &rs = op->residual;
+    const bool res_ok = !rs.data || (rs.dtype == AIVC_BF16 && rs.c_off % 8 == 0 && rs.c_stride % 8 == 0 &&
+                                     ((uintptr_t)rs.data & 15) == 0);
+    p.tma_store = (o.dtype == AIVC_BF16 && o.c_off % 8 == 0 && o.c_stride % 8 == 0 && p.ncta % 32 == 0 &&
+                   ((uintptr_t)o.data & 15) == 0 && !op->gate.data && res_ok &&
                    getenv("AIVC_TC3_NO_TMA_STORE") == nullptr) ? 1 : 0;
     if (p.tma_store) {
         const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
@@ -294,17 +445,16 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         void *base = (char *)o.data + ((size_t)o.pad * o.pitch + o.pad) * opix + (size_t)o.c_off * 2;
         if (encode_map(&tmO, base, 3, dims, strides, box, 64, "O/3x3")) return 1;
     }
-    const size_t smem = 1024 + (size_t)NA * A_SLOT + (size_t)p.ng * 3 * p.b_slot + 4 * STAGE_BYTES;
+    const size_t smem = fixed + (size_t)p.ng * 3 * p.b_slot;
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         AIVC_CHECK_CUDA(cudaGetDevice(&dev));
         AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024));
-    const int grid = ntiles < sm_count ? ntiles : sm_count;
-    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_kernel, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, tmO, p));
-    AIVC_CHECK_LAUNCH("conv3x3_tc_kernel");
-    return 0;
+    const int slots = sm_count * (pair ? 2 : 1);
+    const int grid = p.nitems < slots ? p.nitems : slots;
+    const bool res = p.tma_store && rs.data;                 // residual prefetched into registers
+    if (sub == 1) return res ? launch_tc3<1, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<1, false>(tmA, tmB, tmO, p, grid, smem, st);
+    return res ? launch_tc3<2, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<2, false>(tmA, tmB, tmO, p, grid, smem, st);
 }

@@ -201,6 +201,20 @@ __device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, con
     return c;
 }
 
+// post activation of 16 values, the kind decided once (not per element)
+__device__ __forceinline__ void post_apply16(int post, float *v) {
+    if (post == AIVC_POST_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (post == AIVC_POST_LEAKY) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+    } else if (post == AIVC_POST_ROUND_CLAMP) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(rintf(v[i]), -256.f), 255.f);
+    }
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int j0, int act_channels) {
     const float4 *b4 = reinterpret_cast<const float4 *>(sbias + j0);
@@ -343,10 +357,7 @@ __device__ __forceinline__ void epi_values16(float *v, const EpiCtx &c, const fl
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
     }
-    if (c.post != AIVC_POST_NONE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = post_apply(c.post, v[i]);
-    }
+    post_apply16(c.post, v);
     if (c.has_scale) {
         const float4 *s4 = reinterpret_cast<const float4 *>(sscale + j0);
 #pragma unroll
@@ -393,7 +404,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    // immediate barrier ids (1..4): a register id makes ptxas reserve all 16 hardware barriers
+    switch (id) {
+        case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+        case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+    }
 }
 
 // bias / scale staged once per CTA in shared memory (zeros / ones when absent)

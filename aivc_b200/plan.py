@@ -239,7 +239,7 @@ class Plan:
 
     def __init__(self, module, h, w, cin, device, cfg=DEFAULT, src_buf=None, src_c_off=0,
                  dst_into=None, out_scale=None, out_post='none', in_dtype=None, in_embed=None,
-                 pad_cout=0):
+                 pad_cout=0, out_dtype=None, out_pad=0):
         """in_embed=(buffer_channels, offset, weight_scale): the module's `cin` input channels
         are channels [offset, offset+cin) of a wider (zero-padded) pixel of `buffer_channels`
         channels; the first stage's weights are embedded accordingly and scaled.
@@ -271,6 +271,8 @@ class Plan:
             assert last.post == 'none'
             last.post = out_post
         self._choose_engines()
+        if out_dtype is not None and dst_into is None:     # e.g. a bf16, bordered output for a tensor-core consumer
+            self.dst.dtype, self.dst.pad = out_dtype, max(self.dst.pad, out_pad)
         self._assign_buffers(src_buf, src_c_off, dst_into, in_dtype)
         self._materialize()
 
