@@ -139,10 +139,15 @@ __device__ __forceinline__ void chunk32_to_stage(const Tc3Params &p, uint32_t ta
     }
 }
 
-template <int SUB, int ACT, bool RES>
+// PAIR: the CTA is one half of a cta_group::2 pair -- unit u of the loop is the pair's u-th pair of tiles,
+// this CTA takes tile 2u + rank, and the accumulator is released with one (possibly remote) arrive per
+// warp on the LEADER CTA's barrier (`acc_empty_rem`: shared::cluster addresses of the two barriers).
+template <int SUB, int ACT, bool RES, bool PAIR>
 __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
                                               const float *sbias, const float *sscale, uint64_t *acc_full,
-                                              uint64_t *acc_empty, uint32_t tmem_base, int warp, int lane) {
+                                              uint64_t *acc_empty, uint32_t tmem_base, int warp, int lane,
+                                              int first, int stride, int nunits, int rank = 0,
+                                              uint32_t acc_empty_rem0 = 0, uint32_t acc_empty_rem1 = 0) {
     constexpr int TILE_H = Cfg<SUB>::TILE_H;
     const int quarter = warp & 3, team = warp >> 2, j = team >> 1, h = team & 1;
     const int row = quarter * 32 + lane;
@@ -159,12 +164,13 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
     uint8_t *my_stage = stage + team * STAGE_BYTES;
     uint32_t it = 0;
     bool store_pending = false;
-    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+    for (int u = first; u < nunits; u += stride, ++it) {
         const uint32_t buf = it & 1u;
-        const int tile = item / p.nsplit, n0 = (item - tile * p.nsplit) * N;
+        const int tile = PAIR ? 2 * u + rank : u / p.nsplit;
+        const int n0 = PAIR ? 0 : (u - tile * p.nsplit) * N;
         const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
         const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
-        const bool valid = (oy < p.out.h) && (ox < p.out.w);
+        const bool valid = (oy < p.out.h) && (ox < p.out.w);      // (a pair's odd tile past the end: all rows invalid)
         const bool use_res = res_fast && valid;
         ctx.out.c_off = p.out.c_off + n0;
         const __nv_bfloat16 *res_px = use_res ? (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0) : nullptr;
@@ -208,7 +214,14 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
             }
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        if (PAIR) {
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? acc_empty_rem1 : acc_empty_rem0)
+                             : "memory");
+        } else {
+            mbar_arrive(&acc_empty[buf]);
+        }
     }
     if (store_pending && leader) tma_store_wait_read();        // smem must outlive the last store's read
 }
@@ -340,10 +353,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ===================== epilogue (warps 0 .. 8 SUB - 1) =====================
         switch (p.act) {
-            case AIVC_ACT_LEAKY: epilogue_team<SUB, AIVC_ACT_LEAKY, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_RELU: epilogue_team<SUB, AIVC_ACT_RELU, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_SIGMOID: epilogue_team<SUB, AIVC_ACT_SIGMOID, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
-            default: epilogue_team<SUB, AIVC_ACT_NONE, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_LEAKY: epilogue_team<SUB, AIVC_ACT_LEAKY, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            case AIVC_ACT_RELU: epilogue_team<SUB, AIVC_ACT_RELU, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            case AIVC_ACT_SIGMOID: epilogue_team<SUB, AIVC_ACT_SIGMOID, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            default: epilogue_team<SUB, AIVC_ACT_NONE, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
         }
     }
 
@@ -366,6 +379,486 @@ int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o,
     return 0;
 }
 
+// =====================================================================================================
+// cta_group::2 variant of the SUB = 2 kernel: two CTAs of a cluster (one TPC) work on two adjacent 32 x 8
+// pixel tiles in lockstep.  One tcgen05.mma.cta_group::2 (M = 256) covers sub-tile j of BOTH tiles; each
+// CTA stages its own activation patch but only HALF of every weight slice (output channels
+// [64 r, 64 r + 64) for rank r) -- the tensor cores read the other half from the peer's shared memory.
+// Per tile that is 87 + 144 = 231 KB of L2 -> SM traffic instead of 375 KB, and 6 KB instead of 8 KB of
+// shared-memory operand reads per MMA: the single-CTA kernel is bound by exactly those two.
+//   * rank 0 (leader) issues all MMAs; `a_full` / `g_full` live in the leader, every TMA load of either
+//     CTA completes its bytes there (.cta_group::2 loads, peer bit of the barrier address cleared);
+//   * slot releases (`a_empty`, `g_empty`) and `acc_full` reach both CTAs through a multicast commit;
+//   * `acc_empty` of the leader collects one arrive per epilogue warp of both CTAs.
+__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0,
+                                                 int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {       // same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<2>::NTHREADS, 1)
+conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
+    using K = Cfg<2>;
+    constexpr int NTHREADS = K::NTHREADS, TILE_H = K::TILE_H;
+    constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[NA], a_empty[NA], g_full[NG_MAX], g_empty[NG_MAX], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[128], sscale[128];
+
+    uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *g_ring = a_ring + NA * A_SLOT;
+    const uint32_t g_slot = 3u * p.b_slot;
+    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.cout;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1, npairs = (p.nitems + 1) >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NG_MAX; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * K::EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == K::MMA_WARP) {                                // the same warp of both CTAs, collectively
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_slot)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    pdl_launch_dependents();
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
+    tc_fence_before();
+    cluster_sync_all();                                       // barriers of both CTAs initialised, TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_wait_prior_grid();
+
+    if (warp == K::TMA_WARP) {
+        // ===================== TMA producer (both CTAs; bytes land on the leader's barriers) =====================
+        if (lane == 0) {
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
+            for (int u = first; u < npairs; u += stride) {
+                const int tile = 2 * u + (int)rank;
+                const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&a_empty[sa], pa ^ 1u);                  // own slot free (multicast commit)
+                    if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * PATCH_BYTES);
+                    tma_load_3d_pair(a_ring + sa * A_SLOT, &tmA, smem_u32(&a_full[sa]) & 0xFEFFFFFFu, kc * 64,
+                                     x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                    for (int ky = 0; ky < 3; ++ky) {
+                        mbar_wait(&g_empty[sg], pg ^ 1u);
+                        if (rank == 0) mbar_expect_tx(&g_full[sg], 2u * 3u * p.b_bytes);
+                        uint8_t *dst = g_ring + sg * g_slot;
+                        const uint32_t bar = smem_u32(&g_full[sg]) & 0xFEFFFFFFu;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            tma_load_3d_pair(dst + kx * p.b_slot, &tmB, bar, kc * 64, (int)rank * (N / 2), ky * 3 + kx);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == K::MMA_WARP) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            // M = 256 (two CTAs x 128 rows), N = cout; operands as in the single-CTA kernel, B holds N/2 rows
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((256u >> 4) << 24);
+            const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
+            for (int u = first; u < npairs; u += stride, ++it) {
+                const uint32_t buf = it & 1u;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // both CTAs' epilogues drained this buffer
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * 256u;
+                uint32_t accum = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
+                    const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
+                    for (int ky = 0; ky < 3; ++ky) {
+                        mbar_wait(&g_full[sg], pg);
+                        tc_fence_after();
+                        const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint32_t start = a_addr + (uint32_t)((ky + 16 * j) * PATCH_W + kx) * 128u;
+                                const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_bf16_pair(acc + (uint32_t)(j * 128), adesc + (uint64_t)(kk * 2),
+                                                   bdesc + (uint64_t)(kk * 2), idesc, accum | (uint32_t)(kx | kk));
+                            }
+                        }
+                        accum = 1;
+                        umma_commit_pair(&g_empty[sg]);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                    }
+                    umma_commit_pair(&a_empty[sa]);
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                }
+                umma_commit_pair(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 0 .. 15 of both CTAs) =====================
+        uint32_t rem0, rem1;                                  // the leader's acc_empty barriers, cluster addresses
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem0) : "r"(smem_u32(&acc_empty[0])));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem1) : "r"(smem_u32(&acc_empty[1])));
+        switch (p.act) {
+            case AIVC_ACT_LEAKY: epilogue_team<2, AIVC_ACT_LEAKY, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
+            case AIVC_ACT_RELU: epilogue_team<2, AIVC_ACT_RELU, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
+            case AIVC_ACT_SIGMOID: epilogue_team<2, AIVC_ACT_SIGMOID, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
+            default: epilogue_team<2, AIVC_ACT_NONE, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                       // nobody leaves while the peer may still touch its smem / TMEM
+    if (warp == K::MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <bool RES>
+int launch_tc3_pair(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const Tc3Params &p, int grid,
+                    size_t smem, cudaStream_t st) {
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_pair_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         220 * 1024));
+    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_pair_kernel<RES>, dim3(grid), dim3(Cfg<2>::NTHREADS), smem, st, a, b, o, p));
+    AIVC_CHECK_LAUNCH("conv3x3_tc_pair_kernel");
+    return 0;
+}
+
+// =====================================================================================================
+// 3x3 stride-1 convolution + GDN / IGDN (misc_layers.py:113-154) in ONE persistent kernel, built on the
+// 16 x 8 pixel tile so that TMEM holds everything the normalisation needs:
+//     columns [0,256)   acc[buf] = conv(x)                       (main loop, as above; double buffered)
+//     columns [256,384) norm     = (acc+bias)^2 . gamma^T         (8 MMAs per tile)
+//     columns [384,448) (acc+bias)^2 as packed bf16: the A operand of the norm GEMM, read from TMEM
+// Epilogue pass 1 (16 warps, one pixel x N/4 channels per thread) reads acc and writes (acc+bias)^2 back to
+// TMEM (tcgen05.st); the MMA thread multiplies it with gamma (resident in shared memory for the whole
+// kernel) between two weight groups of the NEXT tile's main loop, as soon as the operand is there; pass 2
+// reads acc and norm, applies x * (beta+norm)^-+1/2, residual, post activation, gain, and stores through
+// per-team staging tiles + TMA.
+struct GdnBars {
+    uint64_t a_full[NA], a_empty[NA], g_full[NG_MAX], g_empty[NG_MAX];
+    uint64_t acc_full[2], acc_empty[2], norm_full, norm_empty, xsq_full, xsq_empty, gamma_full;
+};
+
+constexpr int GDN_EPI_WARPS = 16, GDN_THREADS = 32 * (GDN_EPI_WARPS + 2), GDN_TMA_WARP = 16, GDN_MMA_WARP = 17;
+
+template <bool RES>
+__global__ void __launch_bounds__(GDN_THREADS, 1)
+conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmG,
+                      const Tc3Params p, const float *gdn_beta, int inverse) {
+    using K = Cfg<1>;
+    constexpr int NTHREADS = GDN_THREADS, TILE_H = K::TILE_H;
+    constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ GdnBars bars;
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[128], sscale[128], sbeta[128];
+
+    const int N = p.cout, nk = N / 64;                        // norm GEMM: K = N in 64-channel chunks
+    uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *g_ring = a_ring + NA * A_SLOT;
+    const uint32_t g_slot = 3u * p.b_slot;
+    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB
+    uint8_t *gam = stage + 4 * STAGE_BYTES;                   // [nk][N rows][128 B], 128B swizzle (TMA)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(&bars.a_full[s], 1); mbar_init(&bars.a_empty[s], 1); }
+        for (int s = 0; s < NG_MAX; ++s) { mbar_init(&bars.g_full[s], 1); mbar_init(&bars.g_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars.acc_full[s], 1); mbar_init(&bars.acc_empty[s], 32 * GDN_EPI_WARPS); }
+        mbar_init(&bars.norm_full, 1); mbar_init(&bars.norm_empty, 32 * GDN_EPI_WARPS);
+        mbar_init(&bars.xsq_full, 32 * GDN_EPI_WARPS); mbar_init(&bars.xsq_empty, 1); mbar_init(&bars.gamma_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == GDN_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_launch_dependents();
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
+    stage_vec(sbeta, gdn_beta, N, 0.f, tid, NTHREADS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_wait_prior_grid();
+
+    if (warp == GDN_TMA_WARP) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars.gamma_full, (uint32_t)(N * N * 2));             // gamma: once per CTA
+            for (int c = 0; c < nk; ++c) tma_load_2d(gam + (size_t)c * N * 128, &tmG, &bars.gamma_full, c * 64, 0);
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
+            for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x) {
+                const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&bars.a_empty[sa], pa ^ 1u);
+                    mbar_expect_tx(&bars.a_full[sa], PATCH_BYTES);
+                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &bars.a_full[sa], kc * 64, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                    for (int ky = 0; ky < 3; ++ky) {
+                        mbar_wait(&bars.g_empty[sg], pg ^ 1u);
+                        mbar_expect_tx(&bars.g_full[sg], 3u * p.b_bytes);
+                        uint8_t *dst = g_ring + sg * g_slot;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            tma_load_3d(dst + kx * p.b_slot, &tmB, &bars.g_full[sg], kc * 64, 0, ky * 3 + kx);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == GDN_MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(N);
+            const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            // norm(k) = xsq of tile k (TMEM, written by the epilogue) . gamma^T (smem)
+            auto issue_norm = [&](uint32_t k) {
+                if (k == 0) mbar_wait(&bars.gamma_full, 0);
+                mbar_wait(&bars.norm_empty, (k & 1u) ^ 1u);                      // pass 2 of tile k-1 has read norm
+                mbar_wait(&bars.xsq_full, k & 1u);                               // pass 1 of tile k has written x^2
+                tc_fence_after();
+                for (int c = 0; c < nk; ++c) {
+                    const uint64_t bd = make_desc(smem_u32(gam + (size_t)c * N * 128), 128);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ts(tmem_base + 256u, tmem_base + 384u + (uint32_t)((c * 4 + kk) * 8),
+                                     bd + (uint64_t)(kk * 2), idesc, (uint32_t)(c | kk));
+                }
+                umma_commit(&bars.norm_full);
+                umma_commit(&bars.xsq_empty);
+            };
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x, ++it) {
+                const uint32_t buf = it & 1u;
+                // norm(it-1) is slipped in between two weight groups of this tile as soon as the epilogue has
+                // delivered x^2 -- never blocking on it while shared-memory slots wait to be consumed
+                bool norm_pending = it > 0;
+                mbar_wait(&bars.acc_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * 128u;
+                uint32_t accum = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&bars.a_full[sa], pa);
+                    const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
+                    for (int ky = 0; ky < 3; ++ky) {
+                        mbar_wait(&bars.g_full[sg], pg);
+                        tc_fence_after();
+                        const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
+                        if (!(p.dbg & 4))
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
+                            const uint32_t start = a_addr + (uint32_t)(ky * PATCH_W + kx) * 128u;
+                            const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                          accum | (uint32_t)(kx | kk));
+                        }
+                        accum = 1;
+                        umma_commit(&bars.g_empty[sg]);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                        if (norm_pending && mbar_test(&bars.xsq_full, (it - 1) & 1u)) {
+                            issue_norm(it - 1);
+                            norm_pending = false;
+                        }
+                    }
+                    umma_commit(&bars.a_empty[sa]);
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                }
+                umma_commit(&bars.acc_full[buf]);
+                if (norm_pending) issue_norm(it - 1);
+            }
+            if (it > 0) issue_norm(it - 1);
+        }
+    } else {
+        // ===================== epilogue: 4 teams (channel quarters) x 4 lane quarters =====================
+        // sixteen warps, nothing carried in registers between the passes: pass 2 reads acc again (TMEM reads
+        // are cheap), so every thread has N/4 channels of one pixel and plenty of warps hide the latencies
+        const int quarter = warp & 3, team = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const bool leader = quarter == 0 && lane == 0;
+        const int per = N / 4;                                // 32 (N = 128) or 16 (N = 64) channels per thread
+        const int c_lo = team * per;
+        const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint8_t *my_stage = stage + team * STAGE_BYTES;
+        EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr);
+        const bool staged = p.tma_store && per == 32;         // one 32-channel TMA store per team and tile
+        bool store_pending = false;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u;
+            const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
+            const int oy = y0 + row / TILE_W, ox = x0 + row % TILE_W;
+            const bool valid = (oy < p.out.h) && (ox < p.out.w);
+            const bool use_res = RES && valid;
+            const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
+            const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
+            uint4 rr[4];
+            if (RES) {                                          // residual of this thread's channels: issued now,
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);      // consumed in pass 2
+                if (use_res) {
+                    const __nv_bfloat16 *res_px = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, c_lo);
+                    ldg_bf16x16(res_px, rr[0], rr[1]);
+                    if (per == 32) ldg_bf16x16(res_px + 16, rr[2], rr[3]);
+                }
+            }
+            // ---- pass 1: (acc + bias)^2 -> packed bf16 in TMEM (A operand of the norm GEMM)
+            mbar_wait(&bars.acc_full[buf], (it >> 1) & 1u);
+            mbar_wait(&bars.xsq_empty, (it & 1u) ^ 1u);        // norm MMAs of the previous tile have read x^2
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c * 16 < per && !(p.dbg & 2)) {
+                    const int j0 = c_lo + c * 16;
+                    float v[16];
+                    tmem_ld16(tl + buf * 128u + (uint32_t)j0, v);
+                    uint32_t w[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b = *reinterpret_cast<const float4 *>(sbias + j0 + 4 * q);
+                        const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y, x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 * x0, x1 * x1);
+                        const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 * x2, x3 * x3);
+                        w[2 * q] = *reinterpret_cast<const uint32_t *>(&lo);
+                        w[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&hi);
+                    }
+                    tmem_st8(tl + 384u + (uint32_t)(j0 >> 1), w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.xsq_full);
+            // ---- pass 2
+            mbar_wait(&bars.norm_full, it & 1u);
+            tc_fence_after();
+            if (staged && store_pending) {                     // staging tile still being read by the last tile's store?
+                if (leader) tma_store_wait_read();
+                named_bar_sync(1 + team, 128);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c * 16 < per && !(p.dbg & 8)) {
+                    const int j0 = c_lo + c * 16;
+                    float v[16], nr[16];
+                    tmem_ld16(tl + buf * 128u + (uint32_t)j0, v);
+                    tmem_ld16(tl + 256u + (uint32_t)j0, nr);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bi = *reinterpret_cast<const float4 *>(sbias + j0 + 4 * q);
+                        const float4 be = *reinterpret_cast<const float4 *>(sbeta + j0 + 4 * q);
+                        const float bb[4] = {bi.x, bi.y, bi.z, bi.w}, ee[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float xx = v[4 * q + e] + bb[e];
+                            const float t = nr[4 * q + e] + ee[e];
+                            float rs;                                           // MUFU.RSQ: 2^-22 relative, far below bf16
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+                            v[4 * q + e] = inverse ? xx * (t * rs) : xx * rs;
+                        }
+                    }
+                    if (staged) {
+                        if (RES) add_bf16x16(v, rr[2 * c], rr[2 * c + 1]);
+                        post_apply16(p.post, v);
+                        if (p.out_scale) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= sscale[j0 + i];
+                        }
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+                        }
+                        const uint4 lo = make_uint4(w[0], w[1], w[2], w[3]), hi = make_uint4(w[4], w[5], w[6], w[7]);
+                        uint32_t off = (uint32_t)(row * 64 + c * 32);
+                        off ^= ((off >> 7) & 3u) << 4;                  // 64B swizzle, as the TMA store expects
+                        *reinterpret_cast<uint4 *>(my_stage + off) = lo;
+                        *reinterpret_cast<uint4 *>(my_stage + (off ^ 16u)) = hi;
+                        if (edge) border_store_bf16x16(&p, j0, oy, ox, lo, hi);
+                    } else if (valid) {
+                        // generic stores (fp32 / unaligned outputs, slow residuals, gates, 64-channel layers)
+                        epi_tail16(v, ctx, sscale, oy, ox, j0, !edge, out_elem);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars.norm_empty);
+            mbar_arrive(&bars.acc_empty[buf]);
+            if (staged) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + team, 128);
+                if (leader) {
+                    tma_store_3d(&tmO, my_stage, c_lo, x0, y0);
+                    tma_store_commit();
+                }
+                store_pending = true;
+            }
+        }
+        if (store_pending && leader) tma_store_wait_read();    // smem must outlive the last store's read
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == GDN_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <bool RES>
+int launch_tc3_gdn(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const CUtensorMap &g,
+                   const Tc3Params &p, const float *beta, int inverse, int grid, size_t smem, cudaStream_t st) {
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_gdn_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         225 * 1024));
+    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_gdn_kernel<RES>, dim3(grid), dim3(GDN_THREADS), smem, st, a, b, o, g, p,
+                               beta, inverse));
+    AIVC_CHECK_LAUNCH("conv3x3_tc_gdn_kernel");
+    return 0;
+}
+
 }  // namespace
 
 // Returns -1 when the stage does not fit this kernel (caller falls through to the generic one).
@@ -373,7 +866,9 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int cin = op->in.c, cout = op->out.c;
     if (op->kind != 0 || op->k != 3 || op->stride != 1) return -1;
     if (cin % 64 || cout % 16 || cout > 128) return -1;
-    if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN) return -1;
+    const bool gdn = op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN;
+    if (gdn && (cout != 128 && cout != 64)) return -1;
+    if (gdn && getenv("AIVC_TC3_NO_GDN")) return -1;         // A/B switch
     if (op->in.dtype != AIVC_BF16 || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 8) return -1;
     if (op->act_channels) return -1;
     static const int force_sub = getenv("AIVC_TC3_SUB") ? atoi(getenv("AIVC_TC3_SUB")) : 0;   // experiment switch
@@ -382,7 +877,8 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     // per SM and (wide layers) the output channels of a tile split over two work items.
     const int tiles32 = tiles_x * ceil_div(op->out.h, 32);
     int sub = tiles32 >= 296 ? 2 : 1;
-    if (force_sub == 1 || force_sub == 2) sub = force_sub;
+    if (gdn) sub = 1;                                          // conv + GDN kernel: 16-row tiles, one CTA per SM
+    else if (force_sub == 1 || force_sub == 2) sub = force_sub;
     else if (tiles32 >= 148 && tiles32 < 296) return -1;   // one-and-a-bit waves either way: the 128-pixel-tile kernel fills the chip better
     const int tile_h = 16 * sub;
     const int ntiles = tiles_x * ceil_div(op->out.h, tile_h);
@@ -394,19 +890,25 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->gate.data) p.gate = to_dev(op->gate);
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / 64;
-    p.nsplit = (sub == 1 && cout == 128 && ntiles < 296) ? 2 : 1;
+    // cta_group::2 pairs (every CTA stages only half of each weight slice): OPT-IN.  Measured on B200 the
+    // pair kernel is 4-10 % slower than the single-CTA kernel (125 vs 121 us at 540x960, 42 vs 37 us at
+    // 270x480): the single-CTA kernel already runs at ~93 % of cuBLAS' sustained bf16 rate there, so the
+    // halved operand traffic buys nothing and the lockstep of the two CTAs costs a little.
+    const bool pair = sub == 2 && getenv("AIVC_TC3_PAIR") != nullptr && (cout == 128 || cout == 64);
+    p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
     p.ncta = cout / p.nsplit;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.in_pad = op->in.pad;
-    p.b_bytes = (uint32_t)p.ncta * 128u;
+    p.b_bytes = (uint32_t)(pair ? cout / 2 : p.ncta) * 128u;    // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
-    const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES;
+    const size_t gdn_bytes = gdn ? (size_t)cout * cout * 2 + 2 * STAGE_BYTES : 0;   // gamma + two more staging tiles
+    const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES + gdn_bytes;
     // SUB = 1 aims at two CTAs per SM (<= 111 KB each) when two weight groups fit in that
     const size_t two_cta = 111 * 1024;
-    const bool pair = sub == 1 && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
-    const size_t budget = sub == 2 ? 219 * 1024 : (pair ? two_cta : 165 * 1024);
+    const bool two_per_sm = sub == 1 && !gdn && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
+    const size_t budget = sub == 2 ? 219 * 1024 : (two_per_sm ? two_cta : (gdn ? 224 * 1024 : 165 * 1024));
     p.ng = NG_MAX;
     while (fixed + (size_t)p.ng * 3 * p.b_slot > budget && p.ng > 1) --p.ng;
     if (p.ng < 2) return -1;
@@ -423,7 +925,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)p.ncta, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)(pair ? cout / 2 : p.ncta), 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, 128, "B/3x3")) return 1;
     }
     CUtensorMap tmO;
@@ -452,9 +954,25 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         AIVC_CHECK_CUDA(cudaGetDevice(&dev));
         AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int slots = sm_count * (pair ? 2 : 1);
-    const int grid = p.nitems < slots ? p.nitems : slots;
     const bool res = p.tma_store && rs.data;                 // residual prefetched into registers
+    if (gdn) {
+        CUtensorMap tmG;
+        cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)cout * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)cout};
+        if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, 128, "gamma/3x3")) return 1;
+        const int grid = ntiles < sm_count ? ntiles : sm_count;
+        const int inverse = op->act == AIVC_ACT_IGDN ? 1 : 0;
+        return res ? launch_tc3_gdn<true>(tmA, tmB, tmO, tmG, p, op->gdn_beta, inverse, grid, smem, st)
+                   : launch_tc3_gdn<false>(tmA, tmB, tmO, tmG, p, op->gdn_beta, inverse, grid, smem, st);
+    }
+    if (pair) {
+        const int npairs = (ntiles + 1) / 2, nclusters = sm_count / 2;
+        const int grid = 2 * (npairs < nclusters ? npairs : nclusters);
+        return res ? launch_tc3_pair<true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3_pair<false>(tmA, tmB, tmO, p, grid, smem, st);
+    }
+    const int slots = sm_count * (two_per_sm ? 2 : 1);
+    const int grid = p.nitems < slots ? p.nitems : slots;
     if (sub == 1) return res ? launch_tc3<1, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<1, false>(tmA, tmB, tmO, p, grid, smem, st);
     return res ? launch_tc3<2, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<2, false>(tmA, tmB, tmO, p, grid, smem, st);
 }

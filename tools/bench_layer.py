@@ -19,6 +19,7 @@ CASES = {
     'c3_128_68': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='leaky_relu'), 128, 68, 120),
     'c3s2_128_540': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='leaky_relu', conv_stride=2), 128, 540, 960),
     'c3gdn_128_270': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='gdn'), 128, 270, 480),
+    'c3igdn_128_544': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='gdn_inverse'), 128, 544, 960),
     'up3_128_270': (lambda: M.UpscalingLayer(3, 128, 128, non_linearity='leaky_relu'), 128, 270, 480),
     'up5_128_16_544': (lambda: M.UpscalingLayer(5, 128, 16, non_linearity='no'), 128, 544, 960),
     'cheng_plain_270': (lambda: M.ChengResBlock(128, 'plain'), 128, 270, 480),
