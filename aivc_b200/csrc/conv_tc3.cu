@@ -735,16 +735,6 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const bool use_res = RES && valid;
             const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
             const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
-            uint4 rr[4];
-            if (RES) {                                          // residual of this thread's channels: issued now,
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);      // consumed in pass 2
-                if (use_res) {
-                    const __nv_bfloat16 *res_px = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, c_lo);
-                    ldg_bf16x16(res_px, rr[0], rr[1]);
-                    if (per == 32) ldg_bf16x16(res_px + 16, rr[2], rr[3]);
-                }
-            }
             // ---- pass 1: (acc + bias)^2 -> packed bf16 in TMEM (A operand of the norm GEMM)
             mbar_wait(&bars.acc_full[buf], (it >> 1) & 1u);
             mbar_wait(&bars.xsq_empty, (it & 1u) ^ 1u);        // norm MMAs of the previous tile have read x^2
@@ -772,6 +762,16 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_before();
             mbar_arrive(&bars.xsq_full);
             // ---- pass 2
+            uint4 rr[4];
+            if (RES) {                  // residual of this thread's channels: in flight while the norm GEMM runs
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (use_res && !(p.dbg & 128)) {
+                    const __nv_bfloat16 *res_px = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, c_lo);
+                    ldg_bf16x16(res_px, rr[0], rr[1]);
+                    if (per == 32) ldg_bf16x16(res_px + 16, rr[2], rr[3]);
+                }
+            }
             mbar_wait(&bars.norm_full, it & 1u);
             tc_fence_after();
             if (staged && store_pending) {                     // staging tile still being read by the last tile's store?

@@ -313,6 +313,12 @@ class Plan:
                 s.src.dtype = BF16
                 if s.kind == 0 and s.k > 1:
                     s.src.pad = max(s.src.pad, s.k // 2)
+                # skip / trunk tensors that only ever feed an epilogue (ChengResBlock aux path, attention
+                # trunk) are bf16 too: their producers then store through the staged TMA path and the
+                # consumer prefetches them as packed 16-byte groups
+                for t in (s.res, s.gate):
+                    if t is not None and not t.external:
+                        t.dtype = BF16
 
     def _assign_buffers(self, src_buf, src_c_off, dst_into, in_dtype):
         for i, s in enumerate(self.stages):

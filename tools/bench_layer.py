@@ -11,7 +11,18 @@ import aivc_b200.layers as M
 from aivc_b200.plan import Plan, Config
 from aivc_b200._lib import BF16
 
+class _GdnRes(torch.nn.Module):
+    """x + igdn(conv3(x)): the residual flavour of the fused conv + GDN stage (lowered like a ChengResBlock tail)."""
+    def __init__(self, inverse):
+        super().__init__()
+        self.mode = 'plain'
+        self.layers = torch.nn.Sequential(M.CustomConvLayer(3, 128, 128, non_linearity='gdn_inverse' if inverse else 'gdn'))
+_GdnRes.__name__ = 'ChengResBlock'
+
+
 CASES = {
+    'c3igdn_res_544': (lambda: _GdnRes(True), 128, 544, 960),
+    'c3gdn_res_270': (lambda: _GdnRes(False), 128, 270, 480),
     'c3_128_540': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='leaky_relu'), 128, 540, 960),
     'c3_128_270': (lambda: M.CustomConvLayer(3, 128, 128, non_linearity='leaky_relu'), 128, 270, 480),
     'res_128_270': (lambda: M.ResBlock(3, 128), 128, 270, 480),
