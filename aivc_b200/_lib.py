@@ -30,7 +30,8 @@ class ConvOp(C.Structure):
                 ('gdn_beta', C.c_void_p), ('gdn_gamma', C.c_void_p),
                 ('residual', FMap), ('gate', FMap),
                 ('out_scale', C.c_void_p), ('scratch', C.c_void_p),
-                ('act_channels', C.c_int32), ('flags', C.c_int32)]
+                ('act_channels', C.c_int32), ('flags', C.c_int32),
+                ('alg_flops', C.c_double)]
 
 
 OP_LANE1, OP_FORK, OP_JOIN = 1, 2, 4

@@ -6,6 +6,7 @@
 int conv_simt_run(const aivc_conv_op *op, cudaStream_t st);
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st);
 int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st);
+int space_to_depth_run(const aivc_conv_op *op, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 unsigned long long g_aivc_launches = 0;
@@ -17,7 +18,8 @@ static std::vector<StageRec> g_prof;
 static bool g_prof_on = false;
 
 static double stage_flops(const aivc_conv_op *op) {
-    if (op->kind == 2) return 0.0;              // col2im: data movement only
+    if (op->alg_flops > 0.0) return op->alg_flops;
+    if (op->kind >= 2) return 0.0;              // col2im / space-to-depth: data movement only
     const double px = op->kind == 0 ? (double)op->out.h * op->out.w : (double)op->in.h * op->in.w;
     double f = 2.0 * op->k * op->k * op->in.c * op->out.c * px;
     if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN) f += 2.0 * op->out.c * op->out.c * (double)op->out.h * op->out.w;
@@ -43,7 +45,7 @@ int validate_fmap(const aivc_fmap *m, const char *what) {
 static int validate_conv(const aivc_conv_op *op) {
     if (!op) AIVC_FAIL("conv2d_fused: null op");
     if (validate_fmap(&op->in, "conv in") || validate_fmap(&op->out, "conv out")) return 1;
-    if (!op->weight && op->kind != 2) AIVC_FAIL("conv2d_fused: null weight");
+    if (!op->weight && op->kind < 2) AIVC_FAIL("conv2d_fused: null weight");
     if (op->k < 1 || (op->k & 1) == 0) AIVC_FAIL("conv2d_fused: kernel size %d must be odd", op->k);
     if (op->kind == 0) {
         if (op->stride != 1 && op->stride != 2) AIVC_FAIL("conv2d_fused: stride %d unsupported", op->stride);
@@ -52,8 +54,8 @@ static int validate_conv(const aivc_conv_op *op) {
     } else if (op->kind == 1) {
         if (op->stride != 2) AIVC_FAIL("conv2d_fused: transposed conv needs stride 2");
         if (op->out.h != 2 * op->in.h || op->out.w != 2 * op->in.w) AIVC_FAIL("conv2d_fused: transposed output must be exactly 2x");
-    } else if (op->kind == 2) {
-        return 0;                                   // col2im: checked by its launcher
+    } else if (op->kind == 2 || op->kind == 3) {
+        return 0;                                   // col2im / space-to-depth: checked by their launchers
     } else {
         AIVC_FAIL("conv2d_fused: unknown kind %d", op->kind);
     }
@@ -76,18 +78,19 @@ const char *aivc_last_error(void) { return g_err; }
 
 int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
     if (validate_conv(op)) return 1;
-    if (op->kind != 2 && op->engine != AIVC_ENGINE_SIMT && op->engine != AIVC_ENGINE_TC) AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
+    if (op->kind < 2 && op->engine != AIVC_ENGINE_SIMT && op->engine != AIVC_ENGINE_TC) AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
     StageRec r;
     if (g_prof_on) {
         AIVC_CHECK_CUDA(cudaEventCreate(&r.a));
         AIVC_CHECK_CUDA(cudaEventCreate(&r.b));
-        r.engine = op->kind == 2 ? AIVC_ENGINE_SIMT : op->engine;
+        r.engine = op->kind >= 2 ? AIVC_ENGINE_SIMT : op->engine;
         r.flops = stage_flops(op);
         r.kind = op->kind; r.k = op->k; r.stride = op->stride; r.cin = op->in.c; r.cout = op->out.c;
         r.h = op->out.h; r.w = op->out.w; r.act = op->act;
         AIVC_CHECK_CUDA(cudaEventRecord(r.a, (cudaStream_t)stream));
     }
-    const int rc = op->kind == 2 ? col2im_tconv_run(op, (cudaStream_t)stream)
+    const int rc = op->kind == 3 ? space_to_depth_run(op, (cudaStream_t)stream)
+                 : op->kind == 2 ? col2im_tconv_run(op, (cudaStream_t)stream)
                  : op->engine == AIVC_ENGINE_SIMT ? conv_simt_run(op, (cudaStream_t)stream)
                                                   : conv_tc_run(op, (cudaStream_t)stream);
     if (g_prof_on) {

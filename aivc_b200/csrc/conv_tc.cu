@@ -269,8 +269,13 @@ int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, 
 }  // namespace
 
 int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st);
+int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st);
 
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
+    {
+        const int r = conv_tc1_run(op, st);                  // persistent 1x1 kernel
+        if (r >= 0) return r;
+    }
     static const bool no_tc3 = getenv("AIVC_NO_TC3") != nullptr;     // A/B switch for profiling
     if (!no_tc3) {
         const int r = conv_tc3_run(op, st);

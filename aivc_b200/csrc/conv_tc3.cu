@@ -57,6 +57,7 @@ struct Tc3Params {
     uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
     int tma_store;                    // epilogue stores through smem + TMA (bf16, 32-channel multiples)
+    long long *ts;                    // AIVC_TC3_TS: clock64 timeline of CTA 0 (debug)
     int dbg;                          // AIVC_TC3_DBG bits: timing experiments only (wrong results)
 };
 
@@ -736,9 +737,13 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
             const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
             // ---- pass 1: (acc + bias)^2 -> packed bf16 in TMEM (A operand of the norm GEMM)
+            const bool tsw = p.ts && blockIdx.x == 0 && tid == 0 && it < 30;
+            if (tsw) p.ts[it * 8 + 0] = clock64();
             mbar_wait(&bars.acc_full[buf], (it >> 1) & 1u);
+            if (tsw) p.ts[it * 8 + 1] = clock64();
             mbar_wait(&bars.xsq_empty, (it & 1u) ^ 1u);        // norm MMAs of the previous tile have read x^2
             tc_fence_after();
+            if (tsw) p.ts[it * 8 + 2] = clock64();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 if (c * 16 < per && !(p.dbg & 2)) {
@@ -761,6 +766,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.xsq_full);
+            if (tsw) p.ts[it * 8 + 3] = clock64();
             // ---- pass 2
             uint4 rr[4];
             if (RES) {                  // residual of this thread's channels: in flight while the norm GEMM runs
@@ -774,10 +780,12 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             mbar_wait(&bars.norm_full, it & 1u);
             tc_fence_after();
+            if (tsw) p.ts[it * 8 + 4] = clock64();
             if (staged && store_pending) {                     // staging tile still being read by the last tile's store?
                 if (leader) tma_store_wait_read();
                 named_bar_sync(1 + team, 128);
             }
+            if (tsw) p.ts[it * 8 + 5] = clock64();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 if (c * 16 < per && !(p.dbg & 8)) {
@@ -827,6 +835,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_before();
             mbar_arrive(&bars.norm_empty);
             mbar_arrive(&bars.acc_empty[buf]);
+            if (tsw) p.ts[it * 8 + 6] = clock64();
             if (staged) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 named_bar_sync(1 + team, 128);
@@ -836,6 +845,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 store_pending = true;
             }
+            if (tsw) p.ts[it * 8 + 7] = clock64();
         }
         if (store_pending && leader) tma_store_wait_read();    // smem must outlive the last store's read
     }
@@ -902,6 +912,20 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.b_bytes = (uint32_t)(pair ? cout / 2 : p.ncta) * 128u;    // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
+    static long long *ts_buf = nullptr;
+    if (getenv("AIVC_TC3_TS")) {
+        if (!ts_buf) { cudaMallocManaged(&ts_buf, 240 * sizeof(long long)); }
+        else {                                               // dump the previous launch's timeline
+            cudaDeviceSynchronize();
+            for (int t = 0; t < 12; ++t) {
+                fprintf(stderr, "ts tile %2d:", t);
+                for (int k = 1; k < 8; ++k) fprintf(stderr, " %6lld", ts_buf[t * 8 + k] - ts_buf[t * 8 + k - 1]);
+                fprintf(stderr, "  | period %6lld\n", t ? ts_buf[t * 8] - ts_buf[(t - 1) * 8] : 0LL);
+            }
+        }
+        memset(ts_buf, 0, 240 * sizeof(long long));
+        p.ts = ts_buf;
+    }
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
     const size_t gdn_bytes = gdn ? (size_t)cout * cout * 2 + 2 * STAGE_BYTES : 0;   // gamma + two more staging tiles
     const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES + gdn_bytes;

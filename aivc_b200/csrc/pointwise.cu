@@ -365,6 +365,25 @@ __global__ void pack_weight_kernel(const float *__restrict__ src, void *__restri
     }
 }
 
+
+// kind 3: space-to-depth repack of a bf16 map whose pixels are 16-byte multiples (see aivc_b200.h).
+// One thread per (output pixel incl. border, dy, dx): copies in.c channels.
+__global__ void space_to_depth_kernel(FMap in, FMap out) {
+    const int vec = in.c / 8;                                  // uint4 per source pixel
+    const size_t n = (size_t)(out.h + 2 * out.pad) * (out.w + 2 * out.pad) * 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i & 3);
+        const size_t pix = i >> 2;
+        const int px = (int)(pix % (out.w + 2 * out.pad)), py = (int)(pix / (out.w + 2 * out.pad));
+        const int sy = min(max(2 * (py - out.pad) + (q >> 1), 0), in.h - 1);
+        const int sx = min(max(2 * (px - out.pad) + (q & 1), 0), in.w - 1);
+        const uint4 *s = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)in.data + fm_index(in, sy, sx, 0));
+        uint4 *d = reinterpret_cast<uint4 *>((__nv_bfloat16 *)out.data + ((size_t)py * out.pitch + px) * out.c_stride +
+                                             out.c_off + q * in.c);
+        for (int v = 0; v < vec; ++v) d[v] = s[v];
+    }
+}
+
 int grid_for(size_t n) {
     size_t g = (n + PT - 1) / PT;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -379,6 +398,20 @@ int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
     col2im_tconv_kernel<<<grid_for((size_t)op->out.h * op->out.w), PT, 0, st>>>(to_dev(op->in), to_dev(op->out), op->bias,
                                                                                 op->k, op->act);
     AIVC_CHECK_LAUNCH("col2im_tconv");
+    return 0;
+}
+
+
+int space_to_depth_run(const aivc_conv_op *op, cudaStream_t st) {
+    const aivc_fmap &in = op->in, &out = op->out;
+    if (in.dtype != AIVC_BF16 || out.dtype != AIVC_BF16) AIVC_FAIL("space_to_depth: bf16 maps only");
+    if (in.c % 8 || in.c_off % 8 || in.c_stride % 8 || out.c_off % 8 || out.c_stride % 8)
+        AIVC_FAIL("space_to_depth: channel views must be 16-byte multiples");
+    if (out.c != 4 * in.c || out.h != (in.h + 1) / 2 || out.w != (in.w + 1) / 2)
+        AIVC_FAIL("space_to_depth: output must be ceil(h/2) x ceil(w/2) x 4c");
+    const size_t n = (size_t)(out.h + 2 * out.pad) * (out.w + 2 * out.pad) * 4;
+    space_to_depth_kernel<<<grid_for(n), 256, 0, st>>>(to_dev(in), to_dev(out));
+    AIVC_CHECK_LAUNCH("space_to_depth_kernel");
     return 0;
 }
 

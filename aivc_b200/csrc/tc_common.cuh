@@ -267,7 +267,11 @@ __device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int
         const float4 b = b4[q];
         v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
-    if (ACT != AIVC_ACT_NONE) {
+    if (ACT == AIVC_ACT_SIGMOID && act_channels == 0) {
+        // bf16 engine: ex2.approx + rcp.approx (2^-22 relative) instead of expf + IEEE division
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+    } else if (ACT != AIVC_ACT_NONE) {
         if (act_channels == 0 || j0 + 16 <= act_channels) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = act_apply(ACT, v[i]);
@@ -298,24 +302,37 @@ __device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const flo
     }
 }
 
+__device__ __forceinline__ void unpack_bf16x16(const uint4 *rb, float *r) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t w[4] = {rb[h].x, rb[h].y, rb[h].z, rb[h].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            r[8 * h + 2 * q] = __uint_as_float(w[q] << 16);
+            r[8 * h + 2 * q + 1] = __uint_as_float(w[q] & 0xFFFF0000u);
+        }
+    }
+}
+
 __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
-                                           int j0, bool interior, size_t out_elem, const uint4 *rb = nullptr) {
-    if (c.gate.data) {
+                                           int j0, bool interior, size_t out_elem, const uint4 *rb = nullptr,
+                                           const uint4 *gb = nullptr) {
+    if (gb) {                       // gate row prefetched as packed bf16
+        float g[16];
+        unpack_bf16x16(gb, g);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= g[i];
+    } else if (c.gate.data) {
         float g[16];
         load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= g[i];
     }
     if (rb) {                       // residual row prefetched as packed bf16 (see res_prefetch)
+        float r[16];
+        unpack_bf16x16(rb, r);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t w[4] = {rb[h].x, rb[h].y, rb[h].z, rb[h].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                v[8 * h + 2 * q] += __uint_as_float(w[q] << 16);
-                v[8 * h + 2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
-            }
-        }
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
     } else if (c.res.data) {
         float r[16];
         load16(c.res, c.res_vec, oy, ox, j0, 16, r);
@@ -346,22 +363,35 @@ __device__ __forceinline__ void res_fetch16(const EpiCtx &c, size_t res_elem, in
     rb[1] = p[1];
 }
 
+__device__ __forceinline__ void fetch16(const FMap &m, size_t elem, int j0, uint4 *rb) {
+    const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0);
+    rb[0] = p[0];
+    rb[1] = p[1];
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
                                         const EpiCtx &c, int oy, int ox, bool valid, int c_begin = 0) {
     const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
     const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
-    // bf16 residual rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
+    // bf16 residual / gate rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
     // the TMEM load and arithmetic of chunk j
     const bool pipe_res = valid && c.res.data && c.res_vec && c.res.dtype == AIVC_BF16;
+    const bool pipe_gate = valid && c.gate.data && c.gate_vec && c.gate.dtype == AIVC_BF16;
     const size_t res_elem = pipe_res ? fm_index(c.res, oy, ox, 0) : 0;
-    uint4 rb[2], rn[2];
-    if (pipe_res) res_fetch16(c, res_elem, c_begin, rn);
+    const size_t gate_elem = pipe_gate ? fm_index(c.gate, oy, ox, 0) : 0;
+    uint4 rb[2], rn[2], gb[2], gn[2];
+    if (pipe_res) fetch16(c.res, res_elem, c_begin, rn);
+    if (pipe_gate) fetch16(c.gate, gate_elem, c_begin, gn);
 #pragma unroll 1
     for (int j0 = c_begin; j0 < N; j0 += 16) {
         if (pipe_res) {
             rb[0] = rn[0]; rb[1] = rn[1];
-            if (j0 + 16 < N) res_fetch16(c, res_elem, j0 + 16, rn);
+            if (j0 + 16 < N) fetch16(c.res, res_elem, j0 + 16, rn);
+        }
+        if (pipe_gate) {
+            gb[0] = gn[0]; gb[1] = gn[1];
+            if (j0 + 16 < N) fetch16(c.gate, gate_elem, j0 + 16, gn);
         }
         float v[16];
         if (c.dbg & 256) {
@@ -369,7 +399,7 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbia
             for (int i = 0; i < 16; ++i) v[i] = (float)(j0 + i);
         } else tmem_ld16(taddr + (uint32_t)j0, v);
         epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
-        if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem, pipe_res ? rb : nullptr);
+        if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem, pipe_res ? rb : nullptr, pipe_gate ? gb : nullptr);
     }
 }
 

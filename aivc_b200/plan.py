@@ -38,13 +38,15 @@ class Config:
     hyper: str = 'auto'            # precision of h_a / h_s: 'fp32' (exact engine), 'bf16', or
                                    # 'auto' = same as `precision`
     two_lanes: bool = True         # independent branches of attention blocks on two CUDA streams
+    s2d_first: bool = True         # bf16: 5x5 stride-2 pixel-domain first layer as space-to-depth + 3x3 conv
 
     def key(self):
-        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes)
+        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first)
 
     def hyper_cfg(self):
         h = self.precision if self.hyper == 'auto' else self.hyper
-        return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h, two_lanes=self.two_lanes)
+        return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h, two_lanes=self.two_lanes,
+                      s2d_first=self.s2d_first)
 
 
 DEFAULT = Config()
@@ -107,6 +109,7 @@ class Stage:
     cin_off: int = 0                # weight input channel 0 sits at this channel of the source pixel
     w_scale: float = 1.0            # folded into the packed weights (1/255 for level-unit inputs)
     flags: int = 0                  # _lib.OP_LANE1 / OP_FORK / OP_JOIN
+    alg_flops: float = 0.0          # FLOPs of the reference op(s) when the stage was rewritten (0: from geometry)
 
 
 class Graph:
@@ -260,6 +263,8 @@ class Plan:
             self.src.c = buf_c
         if cfg.precision == 'bf16':
             self._split_narrow_tconvs()
+            if in_embed is not None and cfg.s2d_first:
+                self._space_to_depth_first_layer()
         last = self.stages[-1]
         self.out_c = self.dst.c
         if pad_cout and self.dst.c % pad_cout and last.kind != 2:
@@ -296,10 +301,50 @@ class Plan:
                 out.append(s)
         self.stages = out
 
+    def _space_to_depth_first_layer(self):
+        """5x5 stride-2 conv on the 16-channel pixel buffer (CustomConvLayer(5, in, C, stride 2), first
+        layer of g_a / g_a_ref)  ==  3x3 stride-1 conv over the space-to-depth image (2x2 pixel blocks as
+        64 channels): tap (ky, kx) = (2 ty + dy, 2 tx + dx) of the 5x5 kernel becomes channel block
+        (dy, dx) of tap (ty, tx); the 11 positions of the 6x6 footprint outside the 5x5 get zero weights.
+        K grows from 400 to 576, but the stage then runs on the persistent 3x3 kernel (one activation patch
+        for all taps, fused GDN) instead of 25 strided 32-byte-per-pixel TMA gathers."""
+        out = []
+        for s in self.stages:
+            w = s.weight
+            if not (s.src is self.src and s.kind == 0 and s.k == 5 and s.stride == 2 and self.src.c == 16
+                    and w.shape[0] in (64, 128) and s.gate is None):
+                out.append(s)
+                continue
+            cout, cin_w = w.shape[0], w.shape[1]
+            w16 = torch.zeros(cout, 16, 5, 5, dtype=torch.float32)
+            w16[:, s.cin_off:s.cin_off + cin_w] = w.float().cpu() * s.w_scale
+            w3 = torch.zeros(cout, 64, 3, 3, dtype=torch.float32)
+            for ty in range(3):
+                for dy in range(2):
+                    if 2 * ty + dy > 4:
+                        continue
+                    for tx in range(3):
+                        for dx in range(2):
+                            if 2 * tx + dx > 4:
+                                continue
+                            blk = (dy * 2 + dx) * 16
+                            w3[:, blk:blk + 16, ty, tx] = w16[:, :, 2 * ty + dy, 2 * tx + dx]
+            t = T(s.dst.h, s.dst.w, 64)
+            out.append(Stage(3, 1, 1, s.src, t, None, None))
+            px = s.dst.h * s.dst.w
+            flops = 2.0 * 25 * cin_w * cout * px + (2.0 * cout * cout * px if s.gdn is not None else 0.0)
+            out.append(Stage(0, 3, 1, t, s.dst, w3, s.bias, s.act, s.post, s.gdn, s.res, None, s.out_scale,
+                             alg_flops=flops))
+        self.stages = out
+
     # -- engine / dtype / border selection
     def _choose_engines(self):
         tc = self.cfg.precision == 'bf16'
         for s in self.stages:
+            if s.kind == 3:
+                s.engine = ENGINE_SIMT
+                s.src.dtype = s.dst.dtype = BF16
+                continue
             if s.kind == 2:
                 s.engine = ENGINE_SIMT
                 continue
@@ -374,6 +419,9 @@ class Plan:
             op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
             op.flags = s.flags if self.cfg.two_lanes else 0
             op.inp, op.out = s.src.fmap(), s.dst.fmap()
+            op.alg_flops = s.alg_flops
+            if s.kind == 3:
+                continue
             if s.kind == 2:
                 op.act = ACT[s.act]
                 if s.bias is not None:
@@ -436,7 +484,10 @@ class Plan:
         """Algorithmic FLOPs of the reference graph: convs, tconvs and GDN 1x1."""
         f = 0
         for s in self.stages:
-            if s.kind == 2:
+            if s.kind >= 2:
+                continue
+            if s.alg_flops:
+                f += s.alg_flops
                 continue
             px = s.dst.h * s.dst.w if s.kind == 0 else s.src.h * s.src.w
             w_cout, w_cin = (s.weight.shape[0], s.weight.shape[1]) if s.kind == 0 \

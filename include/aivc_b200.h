@@ -73,6 +73,11 @@ typedef struct {
  *                                                        UpscalingLayer   custom_conv_layers.py:183-253
  *   kind 2: col2im of a transposed conv computed as GEMM: in holds k*k*cout channels
  *           P[(ky,kx,co)] per INPUT pixel, out[2iy-pad+ky][2ix-pad+kx][co] = act(bias + sum P)
+ *   kind 3: space-to-depth repack (no arithmetic): out is the half-resolution map whose pixel (by, bx)
+ *           holds the 2x2 block of `in` pixels as channels (dy*2+dx)*in.c + c, pixels outside `in`
+ *           replicated from its edge; out.h = ceil(in.h/2), out.c = 4*in.c, both bf16.  It turns the 5x5
+ *           stride-2 pixel-domain conv (first layer of g_a / g_a_ref) into a 3x3 stride-1 conv over 64
+ *           channels that the persistent tensor-core kernel runs.
  *   out = post( act(conv(in) + bias) * gate + residual ) * out_scale
  */
 typedef struct {
@@ -89,6 +94,8 @@ typedef struct {
     void *scratch;             /* SIMT GDN needs cout*h*w floats; else NULL */
     int32_t act_channels;      /* `act` applies to output channels [0, act_channels); 0 = all */
     int32_t flags;             /* AIVC_OP_* : two-lane execution inside aivc_conv2d_fused_seq */
+    double alg_flops;          /* algorithmic FLOPs of the REFERENCE op(s) this stage stands for (roofline
+                                * accounting); 0 = derive from this stage's own geometry */
 } aivc_conv_op;
 
 /* Independent branches of a block (SimplifiedAttention's trunk and attention paths) run on two
