@@ -35,6 +35,8 @@ class ConvOp(C.Structure):
 
 
 OP_LANE1, OP_FORK, OP_JOIN = 1, 2, 4
+KERNEL_CLASSES = ('conv_simt_kernel', 'conv_tc_kernel', 'conv3x3_tc_kernel', 'conv3x3_tc_gdn_kernel',
+                  'conv1x1_tc_kernel', 'col2im_tconv_kernel', 'space_to_depth_kernel')
 
 
 _lib = None
@@ -47,6 +49,7 @@ _SIGS = {
     'aivc_profile_enable': (C.c_int, [C.c_int]),
     'aivc_profile_read': (C.c_int, [C.POINTER(C.c_double)]),
     'aivc_profile_dump': (C.c_int, [C.c_char_p]),
+    'aivc_profile_read_classes': (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     'aivc_pack_conv_weight': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 4),

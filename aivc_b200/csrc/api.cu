@@ -13,7 +13,8 @@ unsigned long long g_aivc_launches = 0;
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every conv stage
 #include <vector>
-struct StageRec { cudaEvent_t a, b; int engine; double flops; int kind, k, stride, cin, cout, h, w, act; };
+struct StageRec { cudaEvent_t a, b; int engine; double flops; int kind, k, stride, cin, cout, h, w, act, kclass; };
+int g_aivc_kernel_class = 0;     // set by the launchers: which kernel the last stage ran on (AIVC_KC_*)
 static std::vector<StageRec> g_prof;
 static bool g_prof_on = false;
 
@@ -95,6 +96,7 @@ int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
                                                   : conv_tc_run(op, (cudaStream_t)stream);
     if (g_prof_on) {
         AIVC_CHECK_CUDA(cudaEventRecord(r.b, (cudaStream_t)stream));
+        r.kclass = g_aivc_kernel_class;
         g_prof.push_back(r);
     }
     return rc;
@@ -113,12 +115,12 @@ int aivc_profile_enable(int on) {
 int aivc_profile_dump(const char *path) {
     FILE *f = fopen(path, "w");
     if (!f) AIVC_FAIL("profile_dump: cannot open %s", path);
-    fprintf(f, "engine,kind,k,stride,cin,cout,out_h,out_w,act,flops,ms\n");
+    fprintf(f, "engine,kind,k,stride,cin,cout,out_h,out_w,act,flops,ms,kernel\n");
     for (auto &r : g_prof) {
         AIVC_CHECK_CUDA(cudaEventSynchronize(r.b));
         float ms = 0.f;
         AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
-        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.0f,%.6f\n", r.engine, r.kind, r.k, r.stride, r.cin, r.cout, r.h, r.w, r.act, r.flops, ms);
+        fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%.0f,%.6f,%d\n", r.engine, r.kind, r.k, r.stride, r.cin, r.cout, r.h, r.w, r.act, r.flops, ms, r.kclass);
     }
     fclose(f);
     return 0;
@@ -134,6 +136,19 @@ int aivc_profile_read(double *out) {
         AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
         const int o = r.engine == AIVC_ENGINE_TC ? 0 : 3;
         out[o] += ms; out[o + 1] += r.flops; out[o + 2] += 1.0;
+    }
+    return 0;
+}
+
+// per kernel class k < n: out[3k] = ms, out[3k+1] = algorithmic flops, out[3k+2] = launches
+int aivc_profile_read_classes(double *out, int n) {
+    for (int i = 0; i < 3 * n; ++i) out[i] = 0.0;
+    for (auto &r : g_prof) {
+        AIVC_CHECK_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.kclass < 0 || r.kclass >= n) continue;
+        out[3 * r.kclass] += ms; out[3 * r.kclass + 1] += r.flops; out[3 * r.kclass + 2] += 1.0;
     }
     return 0;
 }

@@ -9,6 +9,7 @@
 // Replaces: CustomConvLayer / UpscalingLayer / GDN forward
 //           (layers/misc/custom_conv_layers.py:129-253, layers/misc/misc_layers.py:113-154).
 #include "common.cuh"
+extern int g_aivc_kernel_class;
 
 namespace {
 
@@ -149,6 +150,7 @@ int launch(const SimtParams &p, cudaStream_t st) {
 //   tconv: out(2m+py) gets in(m + (py + pad - ky)/2) w[ky] for ky with (py + pad - ky) even,
 //          zero outside the input (PyTorch ConvTranspose2d, pad = (k+1)/2 - 1, output_padding 1)
 int conv_simt_run(const aivc_conv_op *op, cudaStream_t st) {
+    g_aivc_kernel_class = AIVC_KC_SIMT;
     const int k = op->k;
     if (k * k > MAX_TAPS) AIVC_FAIL("conv_simt: kernel size %d unsupported", k);
     const bool has_gdn = (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN);

@@ -21,6 +21,7 @@
 #include "tc_common.cuh"
 
 using namespace tcgen;
+extern int g_aivc_kernel_class;
 
 namespace {
 
@@ -281,6 +282,7 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
         const int r = conv_tc3_run(op, st);
         if (r >= 0) return r;
     }
+    g_aivc_kernel_class = AIVC_KC_TC_GENERIC;
     const int k = op->k, cin = op->in.c, cout = op->out.c;
     if (op->in.dtype != AIVC_BF16) AIVC_FAIL("conv_tc: input feature map must be bf16");
     if (cin % 16 || cout % 16 || cout > 256) AIVC_FAIL("conv_tc: cin %d / cout %d not tileable", cin, cout);

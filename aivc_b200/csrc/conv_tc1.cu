@@ -14,6 +14,7 @@
 #include "tc_common.cuh"
 
 using namespace tcgen;
+extern int g_aivc_kernel_class;
 
 namespace {
 
@@ -330,6 +331,7 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
         AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024 + 512));
+    g_aivc_kernel_class = AIVC_KC_TC1;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     AIVC_CHECK_CUDA(launch_pdl(conv1x1_tc_kernel, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, tmG, tmR, tmO, p));
     AIVC_CHECK_LAUNCH("conv1x1_tc_kernel");

@@ -21,6 +21,7 @@
 #include "tc_common.cuh"
 
 using namespace tcgen;
+extern int g_aivc_kernel_class;
 
 namespace {
 
@@ -979,6 +980,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool res = p.tma_store && rs.data;                 // residual prefetched into registers
+    g_aivc_kernel_class = gdn ? AIVC_KC_TC3_GDN : AIVC_KC_TC3;
     if (gdn) {
         CUtensorMap tmG;
         cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};

@@ -3,6 +3,7 @@
 // One thread per pixel (or per symbol); channel counts here are 1..6 at full resolution and
 // C_y at latent resolution, so the work is a single pass over the data.
 #include "common.cuh"
+extern int g_aivc_kernel_class;
 #include "laplace_cdf.h"
 
 namespace {
@@ -392,6 +393,7 @@ int grid_for(size_t n) {
 }  // namespace
 
 int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
+    g_aivc_kernel_class = AIVC_KC_COL2IM;
     if (op->out.c > 8) AIVC_FAIL("col2im: at most 8 output channels, got %d", op->out.c);
     if (op->in.c < op->k * op->k * op->out.c) AIVC_FAIL("col2im: input has %d channels, needs %d", op->in.c, op->k * op->k * op->out.c);
     if (op->out.h != 2 * op->in.h || op->out.w != 2 * op->in.w) AIVC_FAIL("col2im: output must be exactly 2x");
@@ -403,6 +405,7 @@ int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
 
 
 int space_to_depth_run(const aivc_conv_op *op, cudaStream_t st) {
+    g_aivc_kernel_class = AIVC_KC_S2D;
     const aivc_fmap &in = op->in, &out = op->out;
     if (in.dtype != AIVC_BF16 || out.dtype != AIVC_BF16) AIVC_FAIL("space_to_depth: bf16 maps only");
     if (in.c % 8 || in.c_off % 8 || in.c_stride % 8 || out.c_off % 8 || out.c_stride % 8)

@@ -241,7 +241,10 @@ def run_ours(args):
         if profile:
             out = (C.c_double * 6)()
             _lib.check(L.aivc_profile_read(out))
-            prof = list(out)
+            ncls = len(_lib.KERNEL_CLASSES)
+            cls = (C.c_double * (3 * ncls))()
+            _lib.check(L.aivc_profile_read_classes(cls, ncls))
+            prof = list(out) + list(cls)
             if args.stage_csv and rank == 0:
                 _lib.check(L.aivc_profile_dump(args.stage_csv.encode()))
             L.aivc_profile_enable(0)
@@ -274,8 +277,21 @@ def run_ours(args):
     e2e = frames_per_step * args.steps / (ms_e2e / 1000.0)
     if rank == 0:
         peak_tf, peak_bw, peak_src = peaks()
-        tc_ms, tc_fl, tc_n, si_ms, si_fl, si_n = prof
-        ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        tc_ms, tc_fl, tc_n, si_ms, si_fl, si_n = prof[:6]
+        ach_all = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        # per kernel: algorithmic FLOPs of its launches / their CUDA-event durations
+        by_kernel, all_ms = {}, sum(prof[6 + 3 * k] for k in range(len(_lib.KERNEL_CLASSES)))
+        for k, name in enumerate(_lib.KERNEL_CLASSES):
+            k_ms, k_fl, k_n = prof[6 + 3 * k: 9 + 3 * k]
+            if k_n:
+                by_kernel[name] = {'launches_per_step': k_n / args.steps, 'avg_launch_us': 1e3 * k_ms / k_n,
+                                   'tflops': k_fl / (k_ms * 1e-3) / 1e12, 'share_of_stage_time': k_ms / all_ms}
+        dom = max((n for n in by_kernel if by_kernel[n]['tflops'] > 0), key=lambda n: by_kernel[n]['share_of_stage_time'])
+        ach = by_kernel[dom]['tflops']
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')     # dram bytes per launch from the ncu --set full captures
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -288,11 +304,17 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'roofline': {
                 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
-                'traffic': None, 'peak_source': peak_src,
-                'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM conv/tconv + fused epilogue)',
-                'how': 'sum of algorithmic FLOPs of all %d tcgen05 stages of K timed steps / sum of their '
-                       'CUDA-event durations on the launching stream (second pass of the same K steps, '
-                       'events enabled)' % int(tc_n),
+                'traffic': traffic, 'peak_source': peak_src,
+                'kernel': dom + ' (the kernel with the largest share of GPU time)',
+                'how': 'algorithmic FLOPs of this kernel\'s launches in K timed steps / sum of their CUDA-event '
+                       'durations on the launching stream (second pass of the same K steps, an event pair '
+                       'around every convolution stage); `traffic` = DRAM bytes of one representative launch '
+                       '(ncu --set full, profiles/)',
+                'launches_per_step': by_kernel[dom]['launches_per_step'],
+                'avg_launch_us': by_kernel[dom]['avg_launch_us'],
+                'share_of_stage_time': by_kernel[dom]['share_of_stage_time'],
+                'by_kernel': by_kernel,
+                'all_tensor_stages': {'tflops': ach_all, 'frac': ach_all / peak_tf, 'stages': int(tc_n)},
                 'tc_ms_per_step': tc_ms / args.steps, 'tc_share_of_step': tc_ms / ms_prof,
                 'profiled_ms_per_step': ms_prof / args.steps,
                 'simt_ms_per_step': si_ms / args.steps, 'simt_tflops': si_fl / max(si_ms, 1e-9) / 1e9,

@@ -116,8 +116,21 @@ const char *aivc_last_error(void);
 unsigned long long aivc_launch_count(void);
 int aivc_profile_enable(int on);
 int aivc_profile_read(double *out);
-/* one CSV line per recorded stage (engine, geometry, flops, ms) */
+/* one CSV line per recorded stage (engine, geometry, flops, ms, kernel class) */
 int aivc_profile_dump(const char *path);
+/* kernel classes of the recorded stages (which kernel a stage ran on) */
+enum {
+    AIVC_KC_SIMT = 0,        /* conv_simt_kernel (exact fp32) */
+    AIVC_KC_TC_GENERIC = 1,  /* conv_tc_kernel: any k / stride / transposed phases, 128-pixel tiles */
+    AIVC_KC_TC3 = 2,         /* conv3x3_tc_kernel: persistent 3x3 stride-1 (32x8 or 16x8 pixel tiles) */
+    AIVC_KC_TC3_GDN = 3,     /* conv3x3_tc_gdn_kernel: persistent 3x3 + GDN / IGDN */
+    AIVC_KC_TC1 = 4,         /* conv1x1_tc_kernel: persistent 1x1 with TMA-staged gate / residual */
+    AIVC_KC_COL2IM = 5,      /* col2im_tconv_kernel */
+    AIVC_KC_S2D = 6,         /* space_to_depth_kernel */
+    AIVC_KC_COUNT = 7
+};
+/* per kernel class k < n: out[3k] = ms, out[3k+1] = algorithmic flops, out[3k+2] = stages */
+int aivc_profile_read_classes(double *out, int n);
 
 /* ---- convolution stack ------------------------------------------------------------- */
 /* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or
