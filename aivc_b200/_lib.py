@@ -70,6 +70,7 @@ _SIGS = {
     'aivc_quantize_latent': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(FMap), C.c_void_p]),
     'aivc_laplace_scale': (C.c_int, [C.POINTER(FMap), C.c_int, C.c_void_p, C.c_void_p]),
+    'aivc_laplace_window': (C.c_int, [C.POINTER(FMap), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'aivc_dequantize_latent': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p, C.POINTER(FMap),
                                          C.c_void_p]),
     'aivc_fmap_to_i16': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
@@ -82,6 +83,8 @@ _SIGS = {
     'aivc_rc_decode_table': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t,
                                        C.c_void_p]),
     'aivc_rc_decode_laplace': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    'aivc_rc_decode_laplace_win': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                           C.c_void_p]),
     'aivc_laplace_cdf_int_host': (C.c_uint32, [C.c_float, C.c_int]),
     'aivc_sigma_from_logvar_host': (C.c_float, [C.c_float]),
 }

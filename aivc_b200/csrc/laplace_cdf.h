@@ -40,6 +40,7 @@
 #define AIVC_AC_MAX_VAL 256
 #define AIVC_AC_LP 514            /* 2*AC_MAX_VAL + 2, bitstream.py:134 */
 #define AIVC_CDF_SCALE 65023.0f   /* 2^16 - (Lp - 1) */
+#define AIVC_WIN_FIRST 253        /* first CDF entry of the 8-entry window handed to the host decoder */
 #define AIVC_SQRT2_F 1.41421354f  /* fp32 sqrt(2), as torch.sqrt(torch.tensor([2.0])) */
 
 // e^x = 2^k (1 + p): k = rint(x*log2e), r = x - k*ln2 (two-part ln2), p = Taylor(12)(r) - 1.

@@ -296,6 +296,26 @@ __global__ void laplace_scale_kernel(FMap hs, int c, float *__restrict__ b) {
     }
 }
 
+// Decoder side: besides the scale b, the eight integer CDF entries i = 253..260 (the bounds of the symbols
+// q = -3..+3 around the mode) of every symbol, so that the host range decoder resolves almost every
+// symbol with one 16-byte load instead of evaluating the Laplace CDF two or three times.
+__global__ void laplace_window_kernel(FMap hs, int c, float *__restrict__ b, uint4 *__restrict__ win) {
+    const int hw = hs.h * hs.w;
+    const size_t n = (size_t)c * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c), pix = (int)(i / c);
+        const float sigma = aivc_sigma_from_logvar(fm_load(hs, pix / hs.w, pix % hs.w, c + ch));
+        const float bb = aivc_laplace_scale(sigma);
+        uint32_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = aivc_laplace_cdf_int(bb, AIVC_WIN_FIRST + j);
+        const size_t o = (size_t)ch * hw + pix;
+        b[o] = bb;
+        win[o] = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    }
+}
+
 __global__ void dequantize_latent_kernel(const int16_t *__restrict__ q, FMap hs,
                                          const float *__restrict__ dec_gain, FMap yhat) {
     const int c = yhat.c, hw = yhat.h * yhat.w;
@@ -562,6 +582,16 @@ int aivc_laplace_scale(const aivc_fmap *hs, int c, float *b, void *stream) {
     laplace_scale_kernel<<<grid_for((size_t)c * hs->h * hs->w), PT, 0, (cudaStream_t)stream>>>(
         to_dev(*hs), c, b);
     AIVC_CHECK_LAUNCH("laplace_scale");
+    return 0;
+}
+
+int aivc_laplace_window(const aivc_fmap *hs, int c, float *b, uint16_t *win, void *stream) {
+    if (validate_fmap(hs, "laplace_window hs")) return 1;
+    if (hs->c < 2 * c) AIVC_FAIL("laplace_window: need 2C channels");
+    if ((uintptr_t)win & 15) AIVC_FAIL("laplace_window: window buffer must be 16-byte aligned");
+    laplace_window_kernel<<<grid_for((size_t)c * hs->h * hs->w), PT, 0, (cudaStream_t)stream>>>(
+        to_dev(*hs), c, b, reinterpret_cast<uint4 *>(win));
+    AIVC_CHECK_LAUNCH("laplace_window");
     return 0;
 }
 

@@ -254,4 +254,29 @@ int aivc_rc_decode_laplace(const float *b, const uint8_t *in, size_t in_len, siz
     return 0;
 }
 
+
+// As aivc_rc_decode_laplace, with the device-evaluated CDF window win[8 n] (entries 253..260 of every
+// symbol): the analytic search only runs for symbols outside q = -3..+3.
+int aivc_rc_decode_laplace_win(const float *b, const uint16_t *win, const uint8_t *in, size_t in_len, size_t n,
+                               int16_t *sym) {
+    Decoder d(in, in_len);
+    for (size_t i = 0; i < n; ++i) {
+        const uint16_t *w = win + 8 * i;
+        const uint32_t t = d.target();
+        uint32_t lo, hi;
+        int v;
+        if (t >= w[0] && t < w[7]) {
+            int j = 3;                                   // q = 0 first: cdf(256) <= t < cdf(257)
+            if (t < w[3]) { j = 2; while (t < w[j]) --j; }
+            else { while (t >= w[j + 1]) ++j; }
+            v = AIVC_WIN_FIRST + j; lo = w[j]; hi = w[j + 1];
+        } else {
+            v = laplace_search(b[i], t, &lo, &hi);
+        }
+        sym[i] = (int16_t)(v - AIVC_AC_MAX_VAL);
+        d.consume(lo, v == AIVC_AC_LP - 2 ? 0x10000u : hi);
+    }
+    return 0;
+}
+
 }  // extern "C"

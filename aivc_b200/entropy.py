@@ -93,16 +93,23 @@ def y_channels(sec):
     return list(sec[1:1 + n]), sec[1 + n:]
 
 
-def decode_y(sec, b_f32, c, h, w):
-    """b_f32: [C, h, w] float32 Laplace scales (host) -> q [C, h, w] int16."""
+def decode_y(sec, b_f32, c, h, w, win_u16=None):
+    """b_f32: [C, h, w] float32 Laplace scales (host), win_u16: optional [C, h, w, 8] uint16 CDF windows
+    from aivc_laplace_window -> q [C, h, w] int16."""
     L = _lib.lib()
     q = np.zeros((c, h, w), dtype=np.int16)
     idx, payload = y_channels(sec)
     if idx:
-        scales = np.ascontiguousarray(b_f32[idx]).reshape(-1)
+        all_ch = len(idx) == c                      # (the usual case: no gather of the per-symbol side data)
+        scales = (b_f32 if all_ch else np.ascontiguousarray(b_f32[idx])).reshape(-1)
         sym = np.empty(scales.size, dtype=np.int16)
         buf = np.frombuffer(payload, dtype=np.uint8) if len(payload) else np.zeros(1, np.uint8)
-        _lib.check(L.aivc_rc_decode_laplace(scales.ctypes.data, buf.ctypes.data, len(payload),
-                                            scales.size, sym.ctypes.data))
+        if win_u16 is not None:
+            win = (win_u16 if all_ch else np.ascontiguousarray(win_u16[idx])).reshape(-1)
+            _lib.check(L.aivc_rc_decode_laplace_win(scales.ctypes.data, win.ctypes.data, buf.ctypes.data,
+                                                    len(payload), scales.size, sym.ctypes.data))
+        else:
+            _lib.check(L.aivc_rc_decode_laplace(scales.ctypes.data, buf.ctypes.data, len(payload),
+                                                scales.size, sym.ctypes.data))
         q[idx] = sym.reshape(len(idx), h, w)
     return q

@@ -200,6 +200,11 @@ int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *d
                          void *stream);
 /* Decoder side: scale b = sigma/sqrt(2) per symbol, fp32 NCHW, for the host range decoder. */
 int aivc_laplace_scale(const aivc_fmap *hs, int c, float *b, void *stream);
+/* Same, plus win[8] per symbol (uint16, NCHW symbol order, 16-byte aligned): the integer CDF entries
+ * 253..260 = bounds of the symbols -3..+3, evaluated with the arithmetic of aivc_laplace_cdf_int_host,
+ * so the host decoder (aivc_rc_decode_laplace_win) searches a 16-byte table for almost every symbol
+ * instead of evaluating the Laplace CDF (bitstream.py:127-184 builds 514 entries per symbol). */
+int aivc_laplace_window(const aivc_fmap *hs, int c, float *b, uint16_t *win, void *stream);
 /* Decoder side: yhat = (q + mu) * dec_gain from host-decoded symbols. */
 int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *dec_gain,
                            const aivc_fmap *yhat, void *stream);
@@ -219,6 +224,8 @@ int aivc_rc_decode_table(const uint16_t *table, const uint8_t *in, size_t in_len
                          int16_t *sym);
 /* 'laplace' mode: per-symbol scale b (from aivc_laplace_scale), symbols out in [-256, 255] */
 int aivc_rc_decode_laplace(const float *b, const uint8_t *in, size_t in_len, size_t n, int16_t *sym);
+int aivc_rc_decode_laplace_win(const float *b, const uint16_t *win, const uint8_t *in, size_t in_len,
+                               size_t n, int16_t *sym);
 /* host evaluation of the integer Laplace CDF (same arithmetic as the device) */
 uint32_t aivc_laplace_cdf_int_host(float b, int i);
 float aivc_sigma_from_logvar_host(float v);

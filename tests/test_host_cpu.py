@@ -71,6 +71,12 @@ def test_rangecoder_matches_oracle_and_roundtrips(seed):
     _lib.check(L.aivc_rc_decode_laplace(b.ctypes.data, buf.ctypes.data, len(ours), n, dec.ctypes.data))
     assert np.array_equal(dec, q)
     assert np.array_equal(O.rc_decode_table(table, ours, n) - 256, q)
+    # the windowed decoder (CDF entries 253..260 handed over by the device) gives the same symbols
+    win = np.ascontiguousarray(table[:, 253:261]).astype(np.uint16)
+    dec2 = np.empty(n, np.int16)
+    _lib.check(L.aivc_rc_decode_laplace_win(b.ctypes.data, win.ctypes.data, buf.ctypes.data, len(ours), n,
+                                            dec2.ctypes.data))
+    assert np.array_equal(dec2, q)
 
 
 def test_host_cdf_equals_oracle_spec():
