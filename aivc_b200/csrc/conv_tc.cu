@@ -271,10 +271,15 @@ int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, 
 
 int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st);
 int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st);
+int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st);
 
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
     {
         const int r = conv_tc1_run(op, st);                  // persistent 1x1 kernel
+        if (r >= 0) return r;
+    }
+    {
+        const int r = tconv_tc3_run(op, st);                 // persistent transposed 3x3 kernel
         if (r >= 0) return r;
     }
     static const bool no_tc3 = getenv("AIVC_NO_TC3") != nullptr;     // A/B switch for profiling

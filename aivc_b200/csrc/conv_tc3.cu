@@ -870,6 +870,249 @@ int launch_tc3_gdn(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap
     return 0;
 }
 
+// =====================================================================================================
+// Transposed 3x3 stride-2 convolution (UpscalingLayer(3, C, C), custom_conv_layers.py:183-253) as ONE
+// persistent kernel.  Output pixel (2y+py, 2x+px) of phase (py,px) sums 1 / 2 / 2 / 4 taps of the
+// input neighbourhood {y, y+1} x {x, x+1}, so all four phases of a 16 x 8 INPUT tile read the same
+// 18 x 10 activation patch (zero fill beyond the image = the transposed conv's implicit padding) and
+// every one of the nine weight slices is used exactly once per tile:
+//     step A  phases (0,0),(0,1): taps (1,1) | (1,0) (1,2)                     -> TMEM regions 0, 1
+//     step B  phases (1,0),(1,1): taps (0,1) (2,1) | (0,0) (0,2) (2,0) (2,2)   -> TMEM regions 2, 3
+// The epilogue drains step A while the tensor pipe runs step B and step B during the next tile's step A.
+// The generic kernel runs the four phases as separate CTAs, each re-loading a 128-pixel tile per tap.
+// Output goes through 5-D TMA stores (c, x parity, x/2, y parity, y/2).
+struct TapT { unsigned char widx, ph, ay, ax; };
+__constant__ TapT c_tconv3_taps[9] = {
+    {4, 0, 0, 0}, {3, 1, 0, 1}, {5, 1, 0, 0},             // step A: (ky,kx) = (1,1) | (1,0) (1,2)
+    {1, 2, 1, 0}, {7, 2, 0, 0}, {0, 3, 1, 1},             // step B, group 1: (0,1) (2,1) | (0,0)
+    {2, 3, 1, 0}, {6, 3, 0, 1}, {8, 3, 0, 0}};            // step B, group 2: (0,2) (2,0) (2,2)
+
+constexpr int TC_NA = 4;                                  // activation patches in flight (two tiles x two chunks)
+
+__device__ __noinline__ void border_store_up_bf16x32(const Tc3Params *p, int ch, int oy, int ox, uint4 a, uint4 b,
+                                                     uint4 c, uint4 d) {
+    const FMap &m = p->out;
+    const int pd = m.pad;
+    const int y0 = (oy == 0) ? 0 : oy + pd, y1 = (oy == m.h - 1) ? oy + 2 * pd : oy + pd;
+    const int x0 = (ox == 0) ? 0 : ox + pd, x1 = (ox == m.w - 1) ? ox + 2 * pd : ox + pd;
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) {
+            if (yy == oy + pd && xx == ox + pd) continue;       // the pixel itself goes out with the TMA store
+            uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride +
+                                                 m.c_off + ch);
+            q[0] = a; q[1] = b; q[2] = c; q[3] = d;
+        }
+}
+
+template <int ACT>
+__device__ __forceinline__ void tconv_epilogue(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
+                                               const float *sbias, uint64_t *acc_full, uint64_t *acc_empty,
+                                               uint32_t tmem_base, int warp, int lane) {
+    const int quarter = warp & 3, team = warp >> 2;           // team = 32-channel quarter of the 128 outputs
+    const int row = quarter * 32 + lane;
+    const bool leader = quarter == 0 && lane == 0;
+    const int j0 = team * 32;
+    uint8_t *my_stage = stage + team * STAGE_BYTES;
+    bool store_pending = false;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x, ++it) {
+        const int y0 = (tile / p.tiles_x) * 16, x0 = (tile % p.tiles_x) * TILE_W;
+        const int iy = y0 + row / TILE_W, ix = x0 + row % TILE_W;
+        const bool valid = 2 * iy < p.out.h && 2 * ix < p.out.w;       // (input pixel inside the image)
+        const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int step = 0; step < 2; ++step) {
+            mbar_wait(&acc_full[step], it & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ph = step * 2 + sub;                 // py = step, px = sub
+                float v[32];
+                {
+                    uint32_t raw[32];
+                    tmem_ld32_nowait(tl + (uint32_t)(ph * 128 + j0), raw);
+                    if (store_pending) {                       // staging tile still being read by the last store?
+                        if (leader) tma_store_wait_read();
+                        named_bar_sync(1 + team, 128);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                }
+                if (sub == 1) {                                // both regions of this step are in registers / stored
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[step]);
+                }
+                if (j0 < p.cout) {
+                    epi_bias_act16<ACT>(v, sbias, j0, 0);
+                    epi_bias_act16<ACT>(v + 16, sbias, j0 + 16, 0);
+                    uint4 o4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * k + 2 * q], v[8 * k + 2 * q + 1]);
+                            w[q] = *reinterpret_cast<const uint32_t *>(&b2);
+                        }
+                        o4[k] = make_uint4(w[0], w[1], w[2], w[3]);
+                        uint32_t off = (uint32_t)(row * 64 + k * 16);
+                        off ^= ((off >> 7) & 3u) << 4;          // 64B swizzle, as the TMA store expects
+                        *reinterpret_cast<uint4 *>(my_stage + off) = o4[k];
+                    }
+                    const int oy = 2 * iy + step, ox = 2 * ix + sub;
+                    if (valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1))
+                        border_store_up_bf16x32(&p, j0, oy, ox, o4[0], o4[1], o4[2], o4[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + team, 128);
+                if (leader && j0 < p.cout) {
+                    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                                     (uint64_t)tmO),
+                                 "r"(smem_u32(my_stage)), "r"(j0), "r"(sub), "r"(x0), "r"(step), "r"(y0)
+                                 : "memory");
+                    tma_store_commit();
+                }
+                store_pending = true;
+            }
+        }
+    }
+    if (store_pending && leader) tma_store_wait_read();
+}
+
+__global__ void __launch_bounds__(Cfg<2>::NTHREADS, 1)
+tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
+    using K1 = Cfg<1>;
+    constexpr int NTHREADS = Cfg<2>::NTHREADS, TMA_WARP = 16, MMA_WARP = 17;
+    constexpr uint32_t A_SLOT = K1::A_SLOT, PATCH_BYTES = K1::PATCH_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[TC_NA], a_empty[TC_NA], g_full[NG_MAX], g_empty[NG_MAX], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[128];
+
+    uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *g_ring = a_ring + TC_NA * A_SLOT;
+    const uint32_t g_slot = 3u * p.b_slot;
+    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.cout;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NG_MAX; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 512); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_launch_dependents();
+    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_wait_prior_grid();
+
+    if (warp == TMA_WARP) {
+        if (lane == 0) {
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
+            for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x) {
+                const int y0 = (tile / p.tiles_x) * 16, x0 = (tile % p.tiles_x) * TILE_W;
+                for (int kc = 0; kc < p.kchunks; ++kc) {      // both chunks' patches stay for the whole tile
+                    mbar_wait(&a_empty[sa], pa ^ 1u);
+                    mbar_expect_tx(&a_full[sa], PATCH_BYTES);
+                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], kc * 64, x0, y0);
+                    if (++sa == TC_NA) { sa = 0; pa ^= 1u; }
+                }
+                for (int g = 0; g < 3; ++g)                    // group 0 = step A, groups 1, 2 = step B
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        if (g == 2 && kc == 0) { /* order: (g1,kc0) (g1,kc1) (g2,kc0) (g2,kc1) */ }
+                        mbar_wait(&g_empty[sg], pg ^ 1u);
+                        mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
+                        uint8_t *dst = g_ring + sg * g_slot;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+                            tma_load_3d(dst + t * p.b_slot, &tmB, &g_full[sg], kc * 64, 0, c_tconv3_taps[g * 3 + t].widx);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(N);
+            const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x, ++it) {
+                uint32_t a_addr[2];
+                const uint32_t sa0 = sa, pa0 = pa;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    a_addr[kc] = smem_u32(a_ring + sa * A_SLOT);
+                    if (++sa == TC_NA) { sa = 0; pa ^= 1u; }
+                }
+                uint32_t started = 0;                          // phases whose region already holds a partial sum
+                for (int g = 0; g < 3; ++g) {
+                    if (g == 0 || g == 1) {                    // a new step starts: its regions must be drained
+                        mbar_wait(&acc_empty[g], (it & 1u) ^ 1u);
+                        tc_fence_after();
+                    }
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        if (g == 0) {                          // first use of this chunk's patch
+                            uint32_t s_ = sa0 + kc, p_ = pa0;
+                            if (s_ >= TC_NA) { s_ -= TC_NA; p_ ^= 1u; }
+                            mbar_wait(&a_full[s_], p_);
+                        }
+                        mbar_wait(&g_full[sg], pg);
+                        tc_fence_after();
+                        const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const TapT tp = c_tconv3_taps[g * 3 + t];
+                            const uint64_t bdesc = make_desc(g_addr + t * p.b_slot, 128);
+                            const uint32_t start = a_addr[kc] + (uint32_t)(tp.ay * PATCH_W + tp.ax) * 128u;
+                            const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
+                            const uint32_t acc = tmem_base + (uint32_t)tp.ph * 128u;
+                            const uint32_t had = (started >> tp.ph) & 1u;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, had | (uint32_t)kk);
+                            started |= 1u << tp.ph;
+                        }
+                        umma_commit(&g_empty[sg]);
+                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                    }
+                    if (g == 0) umma_commit(&acc_full[0]);     // step A complete
+                }
+                umma_commit(&acc_full[1]);                     // step B complete
+                {                                              // the tile's patches are free
+                    uint32_t s_ = sa0;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        umma_commit(&a_empty[s_]);
+                        if (++s_ == TC_NA) s_ = 0;
+                    }
+                }
+            }
+        }
+    } else {
+        switch (p.act) {
+            case AIVC_ACT_LEAKY: tconv_epilogue<AIVC_ACT_LEAKY>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_RELU: tconv_epilogue<AIVC_ACT_RELU>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+            case AIVC_ACT_SIGMOID: tconv_epilogue<AIVC_ACT_SIGMOID>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+            default: tconv_epilogue<AIVC_ACT_NONE>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 }  // namespace
 
 // Returns -1 when the stage does not fit this kernel (caller falls through to the generic one).
@@ -1001,4 +1244,68 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int grid = p.nitems < slots ? p.nitems : slots;
     if (sub == 1) return res ? launch_tc3<1, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<1, false>(tmA, tmB, tmO, p, grid, smem, st);
     return res ? launch_tc3<2, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<2, false>(tmA, tmB, tmO, p, grid, smem, st);
+}
+
+// Transposed 3x3 stride-2 stage on the persistent kernel above; -1 = not eligible.
+int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
+    static const bool off = getenv("AIVC_NO_TCONV3") != nullptr;        // A/B switch
+    if (off) return -1;
+    const int cin = op->in.c, cout = op->out.c;
+    if (op->kind != 1 || op->k != 3 || op->stride != 2) return -1;
+    if (cin % 64 || cin > 128 || cout % 32 || cout > 128) return -1;
+    if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN || op->act_channels) return -1;
+    if (op->residual.data || op->gate.data || op->out_scale || op->post != AIVC_POST_NONE) return -1;
+    const aivc_fmap &in = op->in, &o = op->out;
+    if (in.dtype != AIVC_BF16 || in.c_off % 8 || in.c_stride % 8) return -1;
+    if (o.dtype != AIVC_BF16 || o.c_off % 8 || o.c_stride % 8 || ((uintptr_t)o.data & 15)) return -1;
+    const int tiles_x = ceil_div(in.w, TILE_W), ntiles = tiles_x * ceil_div(in.h, 16);
+    if (ntiles < 120) return -1;                            // tiny maps: the phase-parallel generic kernel fills the chip better
+
+    Tc3Params p;
+    memset(&p, 0, sizeof(p));
+    p.out = to_dev(o);
+    p.bias = op->bias;
+    p.cout = cout; p.ncta = cout; p.nsplit = 1; p.kchunks = cin / 64;
+    p.act = op->act; p.post = op->post;
+    p.tiles_x = tiles_x; p.nitems = ntiles;
+    p.b_bytes = (uint32_t)cout * 128u;
+    p.b_slot = (p.b_bytes + 1023u) & ~1023u;
+    p.ng = 2;
+    const size_t smem = 1024 + (size_t)TC_NA * Cfg<1>::A_SLOT + (size_t)p.ng * 3 * p.b_slot + 4 * STAGE_BYTES;
+
+    CUtensorMap tmA, tmB, tmO;
+    const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
+    {   // interior only: rows / columns beyond the image read as zero (the transposed conv's padding)
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
+        cuuint64_t strides[2] = {pix_b, row_b};
+        cuuint32_t box[3] = {64, PATCH_W, 18};
+        void *base = (char *)in.data + ((size_t)in.pad * in.pitch + in.pad) * pix_b + (size_t)in.c_off * 2;
+        if (encode_map(&tmA, base, 3, dims, strides, box, 128, "A/tconv3")) return 1;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)cout, 1};
+        if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, 128, "B/tconv3")) return 1;
+    }
+    {   // output interior as (c, x parity, x/2, y parity, y/2): one phase of a tile is a {32, 1, 8, 1, 16} box
+        const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
+        cuuint64_t dims[5] = {(cuuint64_t)cout, 2, (cuuint64_t)in.w, 2, (cuuint64_t)in.h};
+        cuuint64_t strides[4] = {opix, 2 * opix, orow, 2 * orow};
+        cuuint32_t box[5] = {32, 1, TILE_W, 1, 16};
+        void *base = (char *)o.data + ((size_t)o.pad * o.pitch + o.pad) * opix + (size_t)o.c_off * 2;
+        if (encode_map(&tmO, base, 5, dims, strides, box, 64, "O/tconv3")) return 1;
+    }
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        AIVC_CHECK_CUDA(cudaGetDevice(&dev));
+        AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    g_aivc_kernel_class = AIVC_KC_TCONV3;
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(tconv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    const int grid = ntiles < sm_count ? ntiles : sm_count;
+    AIVC_CHECK_CUDA(launch_pdl(tconv3x3_tc_kernel, dim3(grid), dim3(Cfg<2>::NTHREADS), smem, st, tmA, tmB, tmO, p));
+    AIVC_CHECK_LAUNCH("tconv3x3_tc_kernel");
+    return 0;
 }

@@ -127,7 +127,8 @@ enum {
     AIVC_KC_TC1 = 4,         /* conv1x1_tc_kernel: persistent 1x1 with TMA-staged gate / residual */
     AIVC_KC_COL2IM = 5,      /* col2im_tconv_kernel */
     AIVC_KC_S2D = 6,         /* space_to_depth_kernel */
-    AIVC_KC_COUNT = 7
+    AIVC_KC_TCONV3 = 7,      /* tconv3x3_tc_kernel: persistent transposed 3x3 stride 2 */
+    AIVC_KC_COUNT = 8
 };
 /* per kernel class k < n: out[3k] = ms, out[3k+1] = algorithmic flops, out[3k+2] = stages */
 int aivc_profile_read_classes(double *out, int n);

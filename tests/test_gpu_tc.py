@@ -92,7 +92,8 @@ def test_wide_layers_vs_oracle(name, size, dev):
     _check(y, ref, tol)
 
 
-@pytest.mark.parametrize('name', ['conv3_s1_leaky_128', 'cheng_plain_128', 'attention_64', 'conv3_s1_relu_32_48'])
+@pytest.mark.parametrize('name', ['conv3_s1_leaky_128', 'cheng_plain_128', 'attention_64', 'conv3_s1_relu_32_48',
+                                  'conv3_s1_gdn_128', 'cheng_down_128', 'up3_no_128', 'cheng_up_64'])
 def test_persistent_3x3_kernel_vs_oracle(name, dev):
     """Maps large enough (>= 120 tiles of 32x8) for the persistent 3x3 kernel: odd sizes, partial
     tiles on both edges, residual / gate / post-activation epilogues, several tiles per CTA."""
