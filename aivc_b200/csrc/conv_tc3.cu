@@ -45,7 +45,7 @@ constexpr int STAGE_BYTES = 128 * 64;   // one team's store staging tile: 128 ro
 constexpr int TILE_W = 8;
 constexpr int PATCH_W = TILE_W + 2;                                             // 10 pixels
 constexpr int NA = 2;               // activation patches in flight
-constexpr int NG_MAX = 4;           // weight groups (3 taps = one kernel row) in flight
+constexpr int NG_MAX = 6;           // weight groups (3 taps = one kernel row) in flight
 
 struct Tc3Params {
     FMap out, res, gate;
@@ -247,6 +247,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.ncta;
+    const bool tsw = p.ts && blockIdx.x == 0 && tid == 0;
+    if (tsw) p.ts[0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -261,6 +263,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tsw) p.ts[1] = clock64();
     pdl_launch_dependents();
     stage_vec(sbias, p.bias, p.cout, 0.f, tid, NTHREADS);     // weights/bias never depend on the prior grid
     stage_vec(sscale, p.out_scale, p.cout, 1.f, tid, NTHREADS);
@@ -268,7 +271,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    if (tsw) p.ts[2] = clock64();
     pdl_wait_prior_grid();                                    // activations / residuals below do
+    if (tsw) p.ts[3] = clock64();
 
     if (warp == K::TMA_WARP) {
         // ===================== TMA producer =====================
@@ -362,20 +367,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     }
 
+    if (tsw) p.ts[4] = clock64();
     tc_fence_before();
     __syncthreads();
+    if (tsw) p.ts[5] = clock64();
     if (warp == K::MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS)
                      : "memory");
     }
+    if (tsw) p.ts[6] = clock64();
 }
 
 template <int SUB, bool RES>
 int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const Tc3Params &p, int grid,
                size_t smem, cudaStream_t st) {
     AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<SUB, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SUB == 1 ? 166 * 1024 : 220 * 1024));
+                                         220 * 1024));
     AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_kernel<SUB, RES>, dim3(grid), dim3(Cfg<SUB>::NTHREADS), smem, st, a, b, o, p));
     AIVC_CHECK_LAUNCH("conv3x3_tc_kernel");
     return 0;
@@ -1133,7 +1141,13 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     int sub = tiles32 >= 296 ? 2 : 1;
     if (gdn) sub = 1;                                          // conv + GDN kernel: 16-row tiles, one CTA per SM
     else if (force_sub == 1 || force_sub == 2) sub = force_sub;
-    else if (tiles32 >= 148 && tiles32 < 296) return -1;   // one-and-a-bit waves either way: the 128-pixel-tile kernel fills the chip better
+    else if (tiles32 >= 148 && tiles32 < 296) {
+        // one-and-a-bit waves of 32-row tiles.  AIVC_TC3_MID: 0 = generic 128-pixel-tile kernel, 1 = 16-row
+        // tiles, 2 = 32-row tiles (experiment switch)
+        static const int mid = getenv("AIVC_TC3_MID") ? atoi(getenv("AIVC_TC3_MID")) : 0;
+        if (mid == 0) return -1;
+        sub = mid;
+    }
     const int tile_h = 16 * sub;
     const int ntiles = tiles_x * ceil_div(op->out.h, tile_h);
 
@@ -1149,34 +1163,42 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     // 270x480): the single-CTA kernel already runs at ~93 % of cuBLAS' sustained bf16 rate there, so the
     // halved operand traffic buys nothing and the lockstep of the two CTAs costs a little.
     const bool pair = sub == 2 && getenv("AIVC_TC3_PAIR") != nullptr && (cout == 128 || cout == 64);
-    p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
+    // small layers (SUB = 1): AIVC_TC3_SMALL = 0 (default): channel split, two CTAs per SM, shallow ring;
+    // 1: no split, one CTA per SM, deep weight ring; 2: split, one CTA per SM, deep ring  (experiment)
+    static const int small_mode = getenv("AIVC_TC3_SMALL") ? atoi(getenv("AIVC_TC3_SMALL")) : 0;
+    p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296 && small_mode != 1) ? 2 : 1;
     p.ncta = cout / p.nsplit;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.in_pad = op->in.pad;
     p.b_bytes = (uint32_t)(pair ? cout / 2 : p.ncta) * 128u;    // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
-    static long long *ts_buf = nullptr;
-    if (getenv("AIVC_TC3_TS")) {
-        if (!ts_buf) { cudaMallocManaged(&ts_buf, 240 * sizeof(long long)); }
+    static long long *ts_dev = nullptr;
+    if (getenv("AIVC_TC3_TS")) {                             // debug: clock64 timeline of CTA 0 (device memory)
+        long long ts_buf[240];
+        if (!ts_dev) cudaMalloc(&ts_dev, sizeof(ts_buf));
         else {                                               // dump the previous launch's timeline
             cudaDeviceSynchronize();
-            for (int t = 0; t < 12; ++t) {
+            cudaMemcpy(ts_buf, ts_dev, sizeof(ts_buf), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "ts kernel: init+alloc %lld, stage+sync %lld, pdl wait %lld, body %lld, sync %lld, dealloc %lld\n",
+                    ts_buf[1] - ts_buf[0], ts_buf[2] - ts_buf[1], ts_buf[3] - ts_buf[2], ts_buf[4] - ts_buf[3],
+                    ts_buf[5] - ts_buf[4], ts_buf[6] - ts_buf[5]);
+            for (int t = 0; t < 12 && getenv("AIVC_TC3_TS_TILES"); ++t) {
                 fprintf(stderr, "ts tile %2d:", t);
                 for (int k = 1; k < 8; ++k) fprintf(stderr, " %6lld", ts_buf[t * 8 + k] - ts_buf[t * 8 + k - 1]);
                 fprintf(stderr, "  | period %6lld\n", t ? ts_buf[t * 8] - ts_buf[(t - 1) * 8] : 0LL);
             }
         }
-        memset(ts_buf, 0, 240 * sizeof(long long));
-        p.ts = ts_buf;
+        cudaMemset(ts_dev, 0, sizeof(ts_buf));
+        p.ts = ts_dev;
     }
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
     const size_t gdn_bytes = gdn ? (size_t)cout * cout * 2 + 2 * STAGE_BYTES : 0;   // gamma + two more staging tiles
     const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES + gdn_bytes;
     // SUB = 1 aims at two CTAs per SM (<= 111 KB each) when two weight groups fit in that
     const size_t two_cta = 111 * 1024;
-    const bool two_per_sm = sub == 1 && !gdn && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
-    const size_t budget = sub == 2 ? 219 * 1024 : (two_per_sm ? two_cta : (gdn ? 224 * 1024 : 165 * 1024));
+    const bool two_per_sm = sub == 1 && !gdn && small_mode == 0 && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
+    const size_t budget = sub == 2 ? 219 * 1024 : (two_per_sm ? two_cta : (gdn ? 224 * 1024 : (small_mode ? 219 * 1024 : 165 * 1024)));
     p.ng = NG_MAX;
     while (fixed + (size_t)p.ng * 3 * p.b_slot > budget && p.ng > 1) --p.ng;
     if (p.ng < 2) return -1;
