@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AIVC_B200_LIB: alternative build of the same ABI (A/B timing of kernel changes on one box)
 LIB_PATH = os.environ.get('AIVC_B200_LIB') or os.path.join(_HERE, 'libaivc_b200.so')
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT = {'no': 0, 'none': 0, 'leaky_relu': 1, 'relu': 2, 'sigmoid': 3, 'gdn': 4, 'gdn_inverse': 5}
 POST = {'none': 0, 'leaky_relu': 1, 'relu': 2, 'round_clamp': 3}
 ENGINE_SIMT, ENGINE_TC = 0, 1

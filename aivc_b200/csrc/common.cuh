@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -49,6 +50,7 @@ __device__ __forceinline__ size_t fm_index(const FMap &m, int y, int x, int ch) 
 __device__ __forceinline__ float fm_load(const FMap &m, int y, int x, int ch) {
     const size_t i = fm_index(m, y, x, ch);
     if (m.dtype == AIVC_F32) return ((const float *)m.data)[i];
+    if (m.dtype == AIVC_F16) return __half2float(((const __half *)m.data)[i]);
     return __bfloat162float(((const __nv_bfloat16 *)m.data)[i]);
 }
 
@@ -56,6 +58,7 @@ __device__ __forceinline__ void fm_store_raw(const FMap &m, int yp, int xp, int 
     // (yp, xp) are coordinates in the padded buffer
     const size_t i = ((size_t)yp * m.pitch + xp) * m.c_stride + m.c_off + ch;
     if (m.dtype == AIVC_F32) ((float *)m.data)[i] = v;
+    else if (m.dtype == AIVC_F16) ((__half *)m.data)[i] = __float2half_rn(v);
     else ((__nv_bfloat16 *)m.data)[i] = __float2bfloat16_rn(v);
 }
 

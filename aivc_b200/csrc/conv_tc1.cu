@@ -27,7 +27,7 @@ struct Tc1Params {
     int cin, cout, kchunks, nch;                              // nch = cout / 32 epilogue chunks
     int act, post;
     int tw, th, tiles_x, ntiles;
-    int has_gate, has_res;
+    int has_gate, has_res, out_f16;
     uint32_t a_bytes, c_bytes;                                // activation tile; one gate/res/out tile (all chunks)
     uint32_t slot_bytes, off_g, off_r, off_o;                 // slot layout (off_o may alias off_g / off_r)
     uint32_t b_bytes;
@@ -123,10 +123,7 @@ __device__ __forceinline__ void epilogue(const Tc1Params &p, const CUtensorMap *
             for (int k = 0; k < 4; ++k) {
                 uint32_t w[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * k + 2 * q], v[8 * k + 2 * q + 1]);
-                    w[q] = *reinterpret_cast<const uint32_t *>(&b2);
-                }
+                for (int q = 0; q < 4; ++q) w[q] = pack16x2(v[8 * k + 2 * q], v[8 * k + 2 * q + 1], p.out_f16 != 0);
                 o4[k] = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4 *>(slot + p.off_o + off[k]) = o4[k];
             }
@@ -240,8 +237,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-bool bf16_chunkable(const aivc_fmap &m) {
-    return m.dtype == AIVC_BF16 && m.c_off % 8 == 0 && m.c_stride % 8 == 0 && ((uintptr_t)m.data & 15) == 0;
+bool bf16_chunkable(const aivc_fmap &m, bool f16_ok = false) {
+    return (m.dtype == AIVC_BF16 || (f16_ok && m.dtype == AIVC_F16)) && m.c_off % 8 == 0 && m.c_stride % 8 == 0 && ((uintptr_t)m.data & 15) == 0;
 }
 
 // interior view of a bordered map as a {channels, w, h} tensor with 32-channel x tw x th boxes
@@ -274,7 +271,7 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->kind != 0 || op->k != 1 || op->stride != 1) return -1;
     if (cin % 64 || cin > 256 || cout % 32 || cout > 256) return -1;
     if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN || op->act_channels) return -1;
-    if (!bf16_chunkable(op->in) || !bf16_chunkable(op->out)) return -1;
+    if (!bf16_chunkable(op->in) || !bf16_chunkable(op->out, true)) return -1;
     const bool has_gate = op->gate.data != nullptr, has_res = op->residual.data != nullptr;
     if (has_gate && !bf16_chunkable(op->gate)) return -1;
     if (has_res && !bf16_chunkable(op->residual)) return -1;
@@ -285,7 +282,7 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cin = cin; p.cout = cout; p.kchunks = cin / 64; p.nch = cout / 32;
     p.act = op->act; p.post = op->post;
-    p.has_gate = has_gate; p.has_res = has_res;
+    p.has_gate = has_gate; p.has_res = has_res; p.out_f16 = op->out.dtype == AIVC_F16;
     pick_tile1(op->out.h, op->out.w, &p.tw, &p.th);
     p.tiles_x = ceil_div(op->out.w, p.tw);
     p.ntiles = p.tiles_x * ceil_div(op->out.h, p.th);

@@ -149,6 +149,15 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 // ------------------------------------------------------------------------------------ epilogue IO
+// two floats -> one 32-bit word of the map's 16-bit type (bf16, or fp16 for the pixel-domain partial sums)
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {
+    if (f16) {
+        const __half2 h2 = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&h2);
+    }
+    const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&b2);
+}
 struct VecInfo {
     bool vec;       // 16-channel groups are 16-byte aligned
 };
@@ -202,10 +211,7 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
         } else {
             uint32_t w[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                w[i] = *reinterpret_cast<const uint32_t *>(&b2);
-            }
+            for (int i = 0; i < 8; ++i) w[i] = pack16x2(v[2 * i], v[2 * i + 1], m.dtype == AIVC_F16);
             for (int yy = y0; yy <= y1; ++yy)
                 for (int xx = x0; xx <= x1; ++xx) {
                     uint4 *q = reinterpret_cast<uint4 *>(
@@ -292,10 +298,7 @@ __device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const flo
     } else {
         uint32_t w[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
-        }
+        for (int i = 0; i < 8; ++i) w[i] = pack16x2(v[2 * i], v[2 * i + 1], m.dtype == AIVC_F16);
         uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem);
         q[0] = make_uint4(w[0], w[1], w[2], w[3]);
         q[1] = make_uint4(w[4], w[5], w[6], w[7]);

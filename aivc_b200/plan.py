@@ -25,9 +25,9 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import FMap, ConvOp, ACT, POST, F32, BF16, ENGINE_SIMT, ENGINE_TC
+from ._lib import FMap, ConvOp, ACT, POST, F32, BF16, F16, ENGINE_SIMT, ENGINE_TC
 
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 
 
 @dataclass
@@ -294,7 +294,7 @@ class Plan:
                     and s.cin_off == 0 and s.w_scale == 1.0):
                 kk = s.k * s.k * cout
                 wp = s.weight.permute(2, 3, 1, 0).reshape(kk, cin, 1, 1).contiguous()
-                p_t = T(s.src.h, s.src.w, -(-kk // 16) * 16)
+                p_t = T(s.src.h, s.src.w, -(-kk // 32) * 32)       # (32-channel chunks of the persistent 1x1 kernel)
                 out.append(Stage(0, 1, 1, s.src, p_t, wp, None, 'no'))
                 out.append(Stage(2, s.k, 2, p_t, s.dst, None, s.bias, s.act))
             else:
@@ -347,6 +347,8 @@ class Plan:
                 continue
             if s.kind == 2:
                 s.engine = ENGINE_SIMT
+                if tc:          # partial sums of the pixel-domain output: fp16 (11-bit mantissa), half the bytes of fp32
+                    s.src.dtype = F16
                 continue
             cin, cout = s.src.c, s.dst.c
             ok = tc and cin % self.cfg.tc_min_cin == 0 and cout % 16 == 0 and cout <= 256
@@ -355,6 +357,7 @@ class Plan:
             s.engine = ENGINE_TC if ok else ENGINE_SIMT
         for s in self.stages:
             if s.engine == ENGINE_TC:
+                assert s.src.dtype != F16
                 s.src.dtype = BF16
                 if s.kind == 0 and s.k > 1:
                     s.src.pad = max(s.src.pad, s.k // 2)

@@ -27,7 +27,9 @@ extern "C" {
 #define AIVC_ABI_VERSION 1
 
 /* ---- data types / enums ------------------------------------------------------------ */
-enum { AIVC_F32 = 0, AIVC_BF16 = 1 };
+enum { AIVC_F32 = 0, AIVC_BF16 = 1,
+       AIVC_F16 = 2 /* only the GEMM form of the output transposed conv (kind 2 input): pixel-domain partial
+                     * sums need the 11-bit mantissa */ };
 
 /* activation applied right after bias (custom_conv_layers.py:155-177, attention.py:82) */
 enum {
@@ -62,7 +64,7 @@ typedef struct {
     int32_t pad;         /* border width */
     int32_t pitch;       /* allocated pixels per row  (>= w + 2*pad) */
     int32_t rows;        /* allocated rows            (>= h + 2*pad) */
-    int32_t dtype;       /* AIVC_F32 | AIVC_BF16 */
+    int32_t dtype;       /* AIVC_F32 | AIVC_BF16 (| AIVC_F16, see above) */
     int32_t _r;
 } aivc_fmap;
 

@@ -39,6 +39,8 @@ CASES = {
     'att_128_270': (lambda: M.SimplifiedAttention(128), 128, 270, 480),
     'att_64_68': (lambda: M.SimplifiedAttention(64), 64, 68, 120),
     'att_128_68': (lambda: M.SimplifiedAttention(128), 128, 68, 120),
+    'up5_128_6_544': (lambda: M.UpscalingLayer(5, 128, 6, non_linearity='no'), 128, 544, 960),
+    'up5_128_3_544': (lambda: M.UpscalingLayer(5, 128, 3, non_linearity='no'), 128, 544, 960),
     'c5s2_16_128_1080': (lambda: M.CustomConvLayer(5, 16, 128, non_linearity='gdn', conv_stride=2), 16, 1080, 1920),
 }
 
