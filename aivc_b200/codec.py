@@ -416,7 +416,9 @@ class FrameCodec:
 
     def _pool(self):
         if getattr(self, '_tp', None) is None:
-            self._tp = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 4))))
+            # one process per GPU: the ranks of a node share its cores for the range coding
+            per_node = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+            self._tp = ThreadPoolExecutor(max_workers=max(2, min(32, (os.cpu_count() or 4) // per_node)))
         return self._tp
 
 

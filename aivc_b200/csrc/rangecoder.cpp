@@ -262,16 +262,19 @@ int aivc_rc_decode_laplace_win(const float *b, const uint16_t *win, const uint8_
     Decoder d(in, in_len);
     for (size_t i = 0; i < n; ++i) {
         const uint16_t *w = win + 8 * i;
-        const uint32_t t = d.target();
+        // target >= c  <=>  floor((X - 1) / span) >= c  <=>  X > c * span   with X = (value - low + 1) << 16:
+        // the window is searched with multiplications; the 64-bit division only runs for outliers
+        const uint64_t span = (uint64_t)d.high - (uint64_t)d.low + 1;
+        const uint64_t X = ((uint64_t)d.value - (uint64_t)d.low + 1) << 16;
         uint32_t lo, hi;
         int v;
-        if (t >= w[0] && t < w[7]) {
-            int j = 3;                                   // q = 0 first: cdf(256) <= t < cdf(257)
-            if (t < w[3]) { j = 2; while (t < w[j]) --j; }
-            else { while (t >= w[j + 1]) ++j; }
+        if (X > w[0] * span && !(X > w[7] * span)) {
+            int j = 3;                                   // q = 0 first: cdf(256) <= target < cdf(257)
+            if (!(X > w[3] * span)) { j = 2; while (!(X > w[j] * span)) --j; }
+            else { while (X > w[j + 1] * span) ++j; }
             v = AIVC_WIN_FIRST + j; lo = w[j]; hi = w[j + 1];
         } else {
-            v = laplace_search(b[i], t, &lo, &hi);
+            v = laplace_search(b[i], d.target(), &lo, &hi);
         }
         sym[i] = (int16_t)(v - AIVC_AC_MAX_VAL);
         d.consume(lo, v == AIVC_AC_LP - 2 ? 0x10000u : hi);
