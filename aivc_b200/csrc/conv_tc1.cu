@@ -27,7 +27,7 @@ struct Tc1Params {
     int cin, cout, kchunks, nch;                              // nch = cout / 32 epilogue chunks
     int act, post;
     int tw, th, tiles_x, ntiles;
-    int has_gate, has_res, out_f16;
+    int has_gate, has_res, out_f16, stride2;
     uint32_t a_bytes, c_bytes;                                // activation tile; one gate/res/out tile (all chunks)
     uint32_t slot_bytes, off_g, off_r, off_o;                 // slot layout (off_o may alias off_g / off_r)
     uint32_t b_bytes;
@@ -190,8 +190,12 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint8_t *slot = slots + (size_t)s * p.slot_bytes;
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], p.a_bytes + (uint32_t)(p.has_gate + p.has_res) * p.c_bytes);
-                for (int kc = 0; kc < p.kchunks; ++kc)
-                    tma_load_3d(slot + (size_t)kc * 128 * 128, &tmA, &full[s], kc * 64, x0, y0);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    if (p.stride2)                             // (c, x parity 0, x/2, y parity 0, y/2) view of the input
+                        tma_load_5d(slot + (size_t)kc * 128 * 128, &tmA, &full[s], kc * 64, 0, x0, 0, y0);
+                    else
+                        tma_load_3d(slot + (size_t)kc * 128 * 128, &tmA, &full[s], kc * 64, x0, y0);
+                }
                 for (int c = 0; c < p.nch; ++c) {
                     if (p.has_gate) tma_load_3d(slot + p.off_g + (size_t)c * (128 * 64), &tmG, &full[s], c * 32, x0, y0);
                     if (p.has_res) tma_load_3d(slot + p.off_r + (size_t)c * (128 * 64), &tmR, &full[s], c * 32, x0, y0);
@@ -268,7 +272,8 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
     static const bool off = getenv("AIVC_NO_TC1") != nullptr;             // A/B switch
     if (off) return -1;
     const int cin = op->in.c, cout = op->out.c;
-    if (op->kind != 0 || op->k != 1 || op->stride != 1) return -1;
+    if (op->kind != 0 || op->k != 1 || (op->stride != 1 && op->stride != 2)) return -1;
+    if (op->stride == 2 && ((op->in.pitch & 1) || (op->in.rows & 1))) return -1;
     if (cin % 64 || cin > 256 || cout % 32 || cout > 256) return -1;
     if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN || op->act_channels) return -1;
     if (!bf16_chunkable(op->in) || !bf16_chunkable(op->out, true)) return -1;
@@ -282,7 +287,7 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cin = cin; p.cout = cout; p.kchunks = cin / 64; p.nch = cout / 32;
     p.act = op->act; p.post = op->post;
-    p.has_gate = has_gate; p.has_res = has_res; p.out_f16 = op->out.dtype == AIVC_F16;
+    p.has_gate = has_gate; p.has_res = has_res; p.out_f16 = op->out.dtype == AIVC_F16; p.stride2 = op->stride == 2;
     pick_tile1(op->out.h, op->out.w, &p.tw, &p.th);
     p.tiles_x = ceil_div(op->out.w, p.tw);
     p.ntiles = p.tiles_x * ceil_div(op->out.h, p.th);
@@ -305,11 +310,19 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
     {
         const aivc_fmap &in = op->in;
         const size_t pix = (size_t)in.c_stride * 2, rowb = (size_t)in.pitch * pix;
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
-        cuuint64_t strides[2] = {pix, rowb};
-        cuuint32_t box[3] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th};
         void *base = (char *)in.data + ((size_t)in.pad * in.pitch + in.pad) * pix + (size_t)in.c_off * 2;
-        if (encode_map(&tmA, base, 3, dims, strides, box, 128, "A/1x1")) return 1;
+        if (op->stride == 1) {
+            cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
+            cuuint64_t strides[2] = {pix, rowb};
+            cuuint32_t box[3] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+            if (encode_map(&tmA, base, 3, dims, strides, box, 128, "A/1x1")) return 1;
+        } else {
+            // stride 2 (ChengResBlock 'down' skip path): the even pixels of the even rows, as a 5-D view
+            cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)((in.w + 1) / 2), 2, (cuuint64_t)((in.h + 1) / 2)};
+            cuuint64_t strides[4] = {pix, 2 * pix, rowb, 2 * rowb};
+            cuuint32_t box[5] = {64, 1, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th};
+            if (encode_map(&tmA, base, 5, dims, strides, box, 128, "A/1x1s2")) return 1;
+        }
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 1};
