@@ -33,7 +33,7 @@ struct Tc1Params {
     uint32_t b_bytes;
 };
 
-__device__ __noinline__ void border_store_chunk32(const FMap *m, int ch, int oy, int ox, uint4 a, uint4 b, uint4 c,
+__device__ __forceinline__ void border_store_chunk32(const FMap *m, int ch, int oy, int ox, uint4 a, uint4 b, uint4 c,
                                                   uint4 d) {
     const int pd = m->pad;
     const int y0 = (oy == 0) ? 0 : oy + pd, y1 = (oy == m->h - 1) ? oy + 2 * pd : oy + pd;

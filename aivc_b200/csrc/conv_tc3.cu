@@ -83,7 +83,7 @@ __device__ __forceinline__ void add_bf16x16(float *v, const uint4 &r0, const uin
 
 // border replicas of an edge pixel (rare: edge tiles only), kept out of line so that its addressing
 // does not cost the hot path registers
-__device__ __noinline__ void border_store_bf16x16(const Tc3Params *p, int ch, int oy, int ox, uint4 lo, uint4 hi) {
+__device__ __forceinline__ void border_store_bf16x16(const Tc3Params *p, int ch, int oy, int ox, uint4 lo, uint4 hi) {
     const FMap &m = p->out;
     const int pd = m.pad;
     const int y0 = (oy == 0) ? 0 : oy + pd, y1 = (oy == m.h - 1) ? oy + 2 * pd : oy + pd;
@@ -897,7 +897,7 @@ __constant__ TapT c_tconv3_taps[9] = {
 
 constexpr int TC_NA = 4;                                  // activation patches in flight (two tiles x two chunks)
 
-__device__ __noinline__ void border_store_up_bf16x32(const Tc3Params *p, int ch, int oy, int ox, uint4 a, uint4 b,
+__device__ __forceinline__ void border_store_up_bf16x32(const Tc3Params *p, int ch, int oy, int ox, uint4 a, uint4 b,
                                                      uint4 c, uint4 d) {
     const FMap &m = p->out;
     const int pd = m.pad;
