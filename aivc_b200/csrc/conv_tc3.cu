@@ -201,7 +201,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
                         chunk32_to_stage<ACT, true>(p, tl, ch0, n0, sbias, sscale, rr,
                                                     (use_res && ch0 + 32 < c_hi) ? res_px + ch0 + 32 : nullptr, oy, ox, edge, my_stage, row);
                     else
-                        epi_row_staged32<ACT>(tl, ch0, sbias + n0, sscale + n0, ctx, oy, ox, valid, !edge, my_stage, row);
+                        chunk32_to_stage<ACT, false>(p, tl, ch0, n0, sbias, sscale, rr, nullptr, oy, ox, edge, my_stage, row);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     named_bar_sync(1 + team, 128);
                     if (leader) {
