@@ -1,6 +1,12 @@
-// Persistent tcgen05 kernel for the layer that carries most of AIVC's FLOPs: 3x3, stride 1,
-// replicate-padded convolution with Cin a multiple of 64 (ChengResBlock / ResBlock /
-// attention trunks; custom_conv_layers.py:40-56, 112-126).
+// Persistent tcgen05 kernels built around ONE shared activation patch per tile:
+//   conv3x3_tc_kernel<SUB,RES>   3x3 stride-1 conv (+ residual)            -- this header
+//   conv3x3_tc_pair_kernel       the same on cta_group::2 CTA pairs (opt-in: measured slower)
+//   conv3x3_tc_gdn_kernel        3x3 stride-1 conv + GDN / IGDN, norm GEMM with its A operand in TMEM
+//   tconv3x3_tc_kernel           transposed 3x3 stride-2 conv, four output phases per patch
+//
+// conv3x3_tc_kernel: the layer that carries most of AIVC's FLOPs: 3x3, stride 1, replicate-padded
+// convolution with Cin a multiple of 64 (ChengResBlock / ResBlock / attention trunks;
+// custom_conv_layers.py:40-56, 112-126).
 //
 // The generic kernel (conv_tc.cu) reloads a 128-pixel A tile for each of the 9 taps and streams
 // the whole 9*Cin x Cout weight matrix per 128 pixels: it is bound by L2->SM bandwidth.  Here
@@ -15,7 +21,7 @@
 //   * barriers are per kernel ROW (3 taps = 24 MMAs): the single MMA-issuing thread spends ~450
 //     cycles per barrier round trip, which per-tap barriers (8 MMAs = 512 cycles) could not hide;
 //   * the CTA is persistent: accumulators are double-buffered in TMEM (2 x 256 columns), the
-//     eight epilogue warps drain tile i while the MMA thread works on tile i + 1.
+//     sixteen epilogue warps drain tile i while the MMA thread works on tile i + 1.
 // Per 256 pixels: A 2 x 43 KB + B 18 x 16 KB = 375 KB of L2 reads (generic kernel: 1152 KB).
 #include <stdlib.h>
 #include "tc_common.cuh"

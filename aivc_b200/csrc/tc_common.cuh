@@ -98,13 +98,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 64 consecutive columns of this thread's TMEM lane in one instruction; the caller waits (tmem_ld_wait)
-__device__ __forceinline__ void tmem_ld64_nowait(uint32_t taddr, uint32_t *r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr));
-}
+// 32 consecutive columns of this thread's TMEM lane in one instruction; the caller waits (tmem_ld_wait)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -129,7 +123,6 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // Programmatic dependent launch: let the next kernel's CTAs start their prologue while this grid
 // drains, and wait for the previous grid (and its memory) before touching dependent data.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -359,13 +352,6 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
     else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
 }
 
-// 16 channels of a residual row as packed bf16 (two 16-byte loads), for software pipelining
-__device__ __forceinline__ void res_fetch16(const EpiCtx &c, size_t res_elem, int j0, uint4 *rb) {
-    const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)c.res.data + res_elem + j0);
-    rb[0] = p[0];
-    rb[1] = p[1];
-}
-
 __device__ __forceinline__ void fetch16(const FMap &m, size_t elem, int j0, uint4 *rb) {
     const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0);
     rb[0] = p[0];
@@ -415,60 +401,6 @@ __device__ __forceinline__ void epi_row_dispatch(int act, uint32_t taddr, int N,
         case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
         case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
         default: epi_row<AIVC_ACT_NONE>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
-    }
-}
-
-// ---- staged epilogue: 32 channels of a row -> bf16 -> 64-byte row of a swizzled (64B mode) smem tile
-// that one thread then hands to a TMA store.  Everything up to the store is epi_tail16 without it.
-__device__ __forceinline__ void epi_values16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
-                                             int j0, bool valid) {
-    if (c.gate.data && valid) {
-        float g[16];
-        load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= g[i];
-    }
-    if (c.res.data && valid) {
-        float r[16];
-        load16(c.res, c.res_vec, oy, ox, j0, 16, r);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += r[i];
-    }
-    post_apply16(c.post, v);
-    if (c.has_scale) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(sscale + j0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 s = s4[q];
-            v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
-        }
-    }
-}
-
-template <int ACT>
-__device__ __forceinline__ void epi_row_staged32(uint32_t taddr, int ch0, const float *sbias, const float *sscale,
-                                                 const EpiCtx &c, int oy, int ox, bool valid, bool interior,
-                                                 uint8_t *stage, int row) {
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int j0 = ch0 + cc * 16;
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)j0, v);
-        epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
-        epi_values16(v, c, sscale, oy, ox, j0, valid);
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            w[i] = *reinterpret_cast<const uint32_t *>(&b2);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t off = (uint32_t)(row * 64 + cc * 32 + h * 16);
-            off ^= ((off >> 7) & 3u) << 4;                      // 64B swizzle, as the TMA store expects
-            *reinterpret_cast<uint4 *>(stage + off) = make_uint4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
-        }
-        if (valid && !interior) store16(c.out, c.out_vec, oy, ox, j0, 16, v);   // border replicas
     }
 }
 

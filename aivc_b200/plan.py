@@ -186,6 +186,25 @@ def _lower_seq(seq, x, g):
     return x
 
 
+def s2d_weights(w16):
+    """[cout, c, 5, 5] stride-2 kernel -> [cout, 4c, 3, 3] stride-1 kernel over the space-to-depth image
+    (channel (dy*2+dx)*c + ch of block (by, bx) = pixel (2by+dy, 2bx+dx)): tap (ky, kx) = (2ty+dy, 2tx+dx);
+    the 11 positions of the 6x6 footprint outside the 5x5 stay zero."""
+    cout, c = w16.shape[0], w16.shape[1]
+    w3 = torch.zeros(cout, 4 * c, 3, 3, dtype=torch.float32)
+    for ty in range(3):
+        for dy in range(2):
+            if 2 * ty + dy > 4:
+                continue
+            for tx in range(3):
+                for dx in range(2):
+                    if 2 * tx + dx > 4:
+                        continue
+                    blk = (dy * 2 + dx) * c
+                    w3[:, blk:blk + c, ty, tx] = w16[:, :, 2 * ty + dy, 2 * tx + dx]
+    return w3
+
+
 def _fold(g, res=None, gate=None, post='none'):
     s = g.stages[-1]
     assert s.res is None and s.gate is None and s.post == 'none', 'epilogue already occupied'
@@ -318,17 +337,7 @@ class Plan:
             cout, cin_w = w.shape[0], w.shape[1]
             w16 = torch.zeros(cout, 16, 5, 5, dtype=torch.float32)
             w16[:, s.cin_off:s.cin_off + cin_w] = w.float().cpu() * s.w_scale
-            w3 = torch.zeros(cout, 64, 3, 3, dtype=torch.float32)
-            for ty in range(3):
-                for dy in range(2):
-                    if 2 * ty + dy > 4:
-                        continue
-                    for tx in range(3):
-                        for dx in range(2):
-                            if 2 * tx + dx > 4:
-                                continue
-                            blk = (dy * 2 + dx) * 16
-                            w3[:, blk:blk + 16, ty, tx] = w16[:, :, 2 * ty + dy, 2 * tx + dx]
+            w3 = s2d_weights(w16)
             t = T(s.dst.h, s.dst.w, 64)
             out.append(Stage(3, 1, 1, s.src, t, None, None))
             px = s.dst.h * s.dst.w

@@ -166,3 +166,26 @@ def test_layers_refuse_cpu():
     import aivc_b200.layers as M
     with pytest.raises(RuntimeError):
         M.CustomConvLayer(3, 4, 4)(torch.zeros(1, 4, 8, 8))
+
+
+@pytest.mark.parametrize('size', [(12, 16), (13, 17), (9, 10)])
+def test_space_to_depth_first_layer_is_the_same_convolution(size):
+    """plan.s2d_weights: replicate-pad(2) + 5x5 stride-2 conv == 3x3 stride-1 conv over the space-to-depth
+    image with per-pixel replicate semantics (what the kind-3 stage + persistent kernel compute)."""
+    import torch
+    import torch.nn.functional as F
+    from aivc_b200.plan import s2d_weights
+    h, w = size
+    g = torch.Generator().manual_seed(h * 100 + w)
+    x = torch.randn(1, 16, h, w, generator=g, dtype=torch.float64)
+    w16 = torch.randn(8, 16, 5, 5, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.pad(x, (2, 2, 2, 2), mode='replicate'), w16, stride=2)
+    hb, wb = (h + 1) // 2, (w + 1) // 2
+    ys = torch.arange(-1, hb + 1)[:, None] * 2 + torch.arange(2)[None, :]          # [hb+2, dy]
+    xs = torch.arange(-1, wb + 1)[:, None] * 2 + torch.arange(2)[None, :]          # [wb+2, dx]
+    ys, xs = ys.clamp(0, h - 1), xs.clamp(0, w - 1)
+    blocks = x[0][:, ys][:, :, :, xs]                                              # [c, hb+2, dy, wb+2, dx]
+    s2d = blocks.permute(2, 4, 0, 1, 3).reshape(1, 64, hb + 2, wb + 2)             # channel = (dy*2+dx)*16 + c
+    out = F.conv2d(s2d, s2d_weights(w16.float()).double())
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)      # (weights pass through fp32)
