@@ -93,6 +93,8 @@ class CondNetEngine:
         self.b_dev = torch.empty(n_y, dtype=torch.float32, **dev)
         self.win_dev = torch.empty(n_y * 8, dtype=torch.int16, **dev)     # uint16 CDF windows (decoder)
         self._slots = []
+        self._side = None
+        self.overlap_shortcut = os.environ.get('AIVC_NO_OVERLAP') is None     # A/B switch
 
     # -- host staging: one pinned slot per latent in flight, so the GPU never waits for the coder
     def slot(self, i):
@@ -120,9 +122,22 @@ class CondNetEngine:
     # ---------------------------------------------------------------- encoder
     def encode_launch(self, sl, frame_type, use_shortcut, first_of_i_frame=False):
         """Enqueue analysis, quantisation and synthesis; symbols / CDF bounds are copied to the
-        pinned slot `sl` asynchronously.  No host synchronisation."""
+        pinned slot `sl` asynchronously.  No host synchronisation.  The shortcut transform g_a_ref does not
+        depend on the analysis side, so it runs on a second stream next to g_a -> h_a -> h_s -> quantise and
+        fills the SMs those leave idle (wave tails, the latency-bound 68x120 stages); g_s joins both."""
         L, st = _lib.lib(), _lib.stream_ptr()
         enc_gain, dec_gain = self.gains[frame_type]
+        main = torch.cuda.current_stream()
+        overlap = self.overlap_shortcut and use_shortcut and self.has_ref
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+            self._fork.record(main)
+            self._side.wait_event(self._fork)
+            with torch.cuda.stream(self._side):
+                self._shortcut(True)
+                self._join.record(self._side)
         self.g_a.ops[len(self.g_a.ops) - 1].out_scale = enc_gain.data_ptr()
         self.g_a.run()
         if self.y_copy:
@@ -142,7 +157,10 @@ class CondNetEngine:
         sl.nz.copy_(self.nz_dev, non_blocking=True)
         sl.event.record()
         sl.first_of_i_frame = first_of_i_frame
-        self._shortcut(use_shortcut)
+        if overlap:
+            main.wait_event(self._join)
+        else:
+            self._shortcut(use_shortcut)
         self.g_s.run()
 
     def encode_finish(self, sl):

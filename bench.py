@@ -228,6 +228,10 @@ def run_ours(args):
         l0 = L.aivc_launch_count()
         if profile:
             L.aivc_profile_enable(1)
+        # per-stage timing needs kernels one at a time: no second stream next to the timed stages
+        # (the library likewise drops its two-lane execution while profiling)
+        overlap = codec.mof.overlap_shortcut
+        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap and not profile
         sampler = ClockSampler(local) if rank == 0 else None
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -248,6 +252,7 @@ def run_ours(args):
             if args.stage_csv and rank == 0:
                 _lib.check(L.aivc_profile_dump(args.stage_csv.encode()))
             L.aivc_profile_enable(0)
+        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
         launches = L.aivc_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev)
