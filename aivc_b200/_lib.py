@@ -61,6 +61,7 @@ _SIGS = {
     'aivc_fmap_copy': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p]),
     'aivc_yuv420_to_fmap': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.POINTER(FMap), C.c_void_p]),
+    'aivc_yuv420_pack16': (C.c_int, [C.c_void_p] * 9 + [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p]),
     'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int, C.c_int] + [C.POINTER(FMap)] * 2
                         + [C.c_void_p]),
     'aivc_warp_blend_nchw': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),

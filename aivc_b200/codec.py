@@ -288,6 +288,20 @@ class FrameCodec:
                                                   1 if self.levels else 0, C.byref(fm),
                                                   _lib.stream_ptr()))
 
+    def _pack16(self, code, prev, nxt, into_codec):
+        """bf16 engine, uint8 planes: [code | prev | next] -> mof_in (and code -> codec_in) in ONE launch.
+        None = the all-zero frame."""
+        ptrs = []
+        for planes in (code, prev, nxt):
+            ptrs += [None, None, None] if planes is None else [p.data_ptr() for p in planes]
+        d1 = self.mof_in.view(0, 16)
+        d2 = self.codec_in.view(0, 16) if into_codec else None
+        _lib.check(_lib.lib().aivc_yuv420_pack16(*ptrs, C.byref(d1), None if d2 is None else C.byref(d2),
+                                                 _lib.stream_ptr()))
+
+    def _fusable(self, *frames):
+        return self.levels and all(f is None or f[0].dtype == torch.uint8 for f in frames)
+
     def _zero_pred(self):
         full = self.codec_in.t.view(self.codec_in.rows, self.codec_in.pitch, self.codec_in.c)
         full[:, :, 3:6].zero_()
@@ -359,13 +373,20 @@ class FrameCodec:
             for i, f in enumerate(coding_order(gop)):
                 e = gop[f]
                 ft = e['type']
-                self._pack(frames[f], self.codec_in, 0)
                 parts = []
+                prev_r = rec.get(e['prev_ref']) if ft != FRAME_I else None
+                next_r = rec.get(e['next_ref']) if ft == FRAME_B else None
+                fused = ft != FRAME_I and self._fusable(frames[f], prev_r, next_r)
+                if fused:        # [code | prev | next] and the CodecNet's code in one launch
+                    self._pack16(frames[f], prev_r, next_r, True)
+                else:
+                    self._pack(frames[f], self.codec_in, 0)
                 if ft == FRAME_I:
                     self._zero_pred()
                 else:
-                    self._pack(frames[f], self.mof_in, 0)
-                    self._refs(ft, rec.get(e['prev_ref']), rec.get(e['next_ref']))
+                    if not fused:
+                        self._pack(frames[f], self.mof_in, 0)
+                        self._refs(ft, prev_r, next_r)
                     sl = self.mof.slot(i)
                     self.mof.encode_launch(sl, ft, ft == FRAME_B)
                     parts.append(pool.submit(self.mof.encode_finish, sl))
@@ -420,7 +441,11 @@ class FrameCodec:
                 if ft == FRAME_I:
                     self._zero_pred()
                 else:
-                    self._refs(ft, rec.get(e['prev_ref']), rec.get(e['next_ref']))
+                    prev_r, next_r = rec.get(e['prev_ref']), rec.get(e['next_ref']) if ft == FRAME_B else None
+                    if self._fusable(prev_r, next_r):
+                        self._pack16(None, prev_r, next_r, False)
+                    else:
+                        self._refs(ft, prev_r, next_r)
                     futs[(f, 0)].result()
                     self.mof.synth_launch(self.mof.slot(i), ft, ft == FRAME_B)
                     self._motion(ft)

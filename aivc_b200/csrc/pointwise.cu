@@ -105,6 +105,43 @@ __global__ void yuv420_to_fmap_kernel(const void *__restrict__ yp, const void *_
     }
 }
 
+
+// Fused InputLayer for the bf16 engine: up to three 4:2:0 frames (code, prev, next; uint8 levels, a null
+// luma pointer = the all-zero frame) -> channels 0..8 of the 16-channel level-unit pixel buffer, border
+// replicas included, channels 9..15 zero: ONE 32-byte store per pixel instead of three launches writing 6
+// bytes each.  `dst2` (optional) receives frame 0 alone in channels 0..2 (CodecNet input; its channels
+// 3..5 are written later by warp_blend, or stay zero for I frames).
+struct PackSrc { const uint8_t *y[3], *u[3], *v[3]; };
+__global__ void yuv420_pack16_kernel(PackSrc s, FMap dst, FMap dst2) {
+    const int P = dst.pad, W = dst.w + 2 * P, H = dst.h + 2 * P, wc = (dst.w + 1) / 2;
+    const size_t n = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int py = (int)(i / W), px = (int)(i % W);
+        const int y = min(max(py - P, 0), dst.h - 1), x = min(max(px - P, 0), dst.w - 1);
+        const size_t li = (size_t)y * dst.w + x, ci = (size_t)(y / 2) * wc + (x / 2);
+        float c[9];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const bool on = s.y[t] != nullptr;
+            c[3 * t] = on ? (float)s.y[t][li] : 0.f;
+            c[3 * t + 1] = on ? (float)s.u[t][ci] : 0.f;
+            c[3 * t + 2] = on ? (float)s.v[t][ci] : 0.f;
+        }
+        auto pk = [](float a, float b) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+            return *reinterpret_cast<const uint32_t *>(&b2);
+        };
+        uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)dst.data + ((size_t)py * dst.pitch + px) * dst.c_stride);
+        q[0] = make_uint4(pk(c[0], c[1]), pk(c[2], c[3]), pk(c[4], c[5]), pk(c[6], c[7]));
+        q[1] = make_uint4(pk(c[8], 0.f), 0u, 0u, 0u);
+        if (dst2.data) {
+            uint4 *q2 = reinterpret_cast<uint4 *>((__nv_bfloat16 *)dst2.data + ((size_t)py * dst2.pitch + px) * dst2.c_stride);
+            q2[0] = make_uint4(pk(c[0], c[1]), pk(c[2], 0.f), 0u, 0u);
+            q2[1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- warp
 // grid_sample(bilinear, border, align_corners=True) at (x + fx, y + fy), following the fp32
 // operation order of func_util/optical_flow.py:28-41 + ATen's grid sampler.
@@ -146,6 +183,10 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
                                   FMap skip, int levels) {
     const int h = pred.h, w = pred.w;
     const size_t n = (size_t)h * w;
+    // both references are channel slices 3..5 / 6..8 of ONE 16-channel bf16 pixel buffer (the bf16 engine's mof_in)
+    const bool fast = prev.dtype == AIVC_BF16 && next.dtype == AIVC_BF16 && prev.data == next.data && prev.c_stride == 16 &&
+                      prev.c_off == 3 && next.c_off == 6 && prev.pad == next.pad && prev.pitch == next.pitch &&
+                      ((uintptr_t)prev.data & 15) == 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(i / w), x = (int)(i % w);
@@ -159,10 +200,40 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
         } else {
             bn = bilerp_setup(x, y, fm_load(mof, y, x, 4), fm_load(mof, y, x, 5), w, h);
         }
+        float a3[3], b3[3];
+        if (fast) {
+            // 16-channel level-unit pixels (prev = channels 3..5, next = 6..8 of the same 32-byte pixel):
+            // one 16-byte load per prev corner, an 8- and a 4-byte load per next corner
+            const __nv_bfloat16 *base = (const __nv_bfloat16 *)prev.data;
+            auto pix = [&](int yy, int xx) { return base + ((size_t)(yy + prev.pad) * prev.pitch + (xx + prev.pad)) * 16; };
+            auto hi16 = [](uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); };
+            auto lo16 = [](uint32_t v) { return __uint_as_float(v << 16); };
+            a3[0] = a3[1] = a3[2] = b3[0] = b3[1] = b3[2] = 0.f;
+            auto tap_prev = [&](int yy, int xx, float wgt) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(pix(yy, xx));          // channels 0..7
+                a3[0] += hi16(v.y) * wgt; a3[1] += lo16(v.z) * wgt; a3[2] += hi16(v.z) * wgt;
+            };
+            auto tap_next = [&](int yy, int xx, float wgt) {
+                const __nv_bfloat16 *q = pix(yy, xx);
+                const uint32_t c67 = *reinterpret_cast<const uint32_t *>(q + 6), c89 = *reinterpret_cast<const uint32_t *>(q + 8);
+                b3[0] += lo16(c67) * wgt; b3[1] += hi16(c67) * wgt; b3[2] += lo16(c89) * wgt;
+            };
+            tap_prev(bp.y0, bp.x0, bp.w00);
+            if (bp.x1 < w) tap_prev(bp.y0, bp.x1, bp.w01);
+            if (bp.y1 < h) tap_prev(bp.y1, bp.x0, bp.w10);
+            if (bp.x1 < w && bp.y1 < h) tap_prev(bp.y1, bp.x1, bp.w11);
+            tap_next(bn.y0, bn.x0, bn.w00);
+            if (bn.x1 < w) tap_next(bn.y0, bn.x1, bn.w01);
+            if (bn.y1 < h) tap_next(bn.y1, bn.x0, bn.w10);
+            if (bn.x1 < w && bn.y1 < h) tap_next(bn.y1, bn.x1, bn.w11);
+        } else {
+            for (int ch = 0; ch < 3; ++ch) {
+                a3[ch] = bilerp_sample(bp, w, h, [&](int yy, int xx) { return fm_load(prev, yy, xx, ch); });
+                b3[ch] = bilerp_sample(bn, w, h, [&](int yy, int xx) { return fm_load(next, yy, xx, ch); });
+            }
+        }
         for (int ch = 0; ch < 3; ++ch) {
-            const float a = bilerp_sample(bp, w, h, [&](int yy, int xx) { return fm_load(prev, yy, xx, ch); });
-            const float b = bilerp_sample(bn, w, h, [&](int yy, int xx) { return fm_load(next, yy, xx, ch); });
-            float xw = beta * a + (1.f - beta) * b;
+            float xw = beta * a3[ch] + (1.f - beta) * b3[ch];
             // level-unit refs/pred (bf16 engine: 8-bit levels are exact in bf16); skip is in [0,1]
             fm_store(pred, y, x, ch, xw * alpha);             // warped_ref * alpha  (decode.py:542)
             if (levels) xw /= 255.f;
@@ -587,6 +658,31 @@ int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, int
     if (u8) yuv420_to_fmap_kernel<true><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst), scale);
     else yuv420_to_fmap_kernel<false><<<g, PT, 0, (cudaStream_t)stream>>>(y, u, v, to_dev(*dst), scale);
     AIVC_CHECK_LAUNCH("yuv420_to_fmap");
+    return 0;
+}
+
+int aivc_yuv420_pack16(const void *y0, const void *u0, const void *v0, const void *y1, const void *u1,
+                       const void *v1, const void *y2, const void *u2, const void *v2, const aivc_fmap *dst,
+                       const aivc_fmap *dst2, void *stream) {
+    if (validate_fmap(dst, "yuv420_pack16 dst")) return 1;
+    if (dst->dtype != AIVC_BF16 || dst->c_stride != 16 || dst->c_off != 0 || ((uintptr_t)dst->data & 15))
+        AIVC_FAIL("yuv420_pack16: destination must be a whole 16-channel bf16 pixel buffer");
+    FMap d2;
+    memset(&d2, 0, sizeof(d2));
+    if (dst2) {
+        if (validate_fmap(dst2, "yuv420_pack16 dst2")) return 1;
+        if (dst2->dtype != AIVC_BF16 || dst2->c_stride != 16 || dst2->c_off != 0 || dst2->h != dst->h || dst2->w != dst->w ||
+            dst2->pad != dst->pad || ((uintptr_t)dst2->data & 15))
+            AIVC_FAIL("yuv420_pack16: second destination must match the first");
+        d2 = to_dev(*dst2);
+    }
+    PackSrc s;
+    s.y[0] = (const uint8_t *)y0; s.u[0] = (const uint8_t *)u0; s.v[0] = (const uint8_t *)v0;
+    s.y[1] = (const uint8_t *)y1; s.u[1] = (const uint8_t *)u1; s.v[1] = (const uint8_t *)v1;
+    s.y[2] = (const uint8_t *)y2; s.u[2] = (const uint8_t *)u2; s.v[2] = (const uint8_t *)v2;
+    const size_t n = (size_t)(dst->h + 2 * dst->pad) * (dst->w + 2 * dst->pad);
+    yuv420_pack16_kernel<<<grid_for(n), PT, 0, (cudaStream_t)stream>>>(s, to_dev(*dst), d2);
+    AIVC_CHECK_LAUNCH("yuv420_pack16");
     return 0;
 }
 

@@ -164,6 +164,14 @@ int aivc_fmap_copy(const aivc_fmap *src, const aivc_fmap *dst, void *stream);
 int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, int levels,
                         const aivc_fmap *dst, void *stream);
 
+/* The same for the bf16 engine's 16-channel level-unit pixel buffers, fused: up to three uint8 4:2:0 frames
+ * (frame to code, previous and next reference; a NULL luma pointer = the all-zero frame, decode.py:710-714)
+ * -> channels 0..8 of `dst` (whole pixel, border replicas included, channels 9..15 zero) in one launch;
+ * `dst2` (optional) receives frame 0 alone in channels 0..2 (CodecNet input [code | pred]). */
+int aivc_yuv420_pack16(const void *y0, const void *u0, const void *v0, const void *y1, const void *u1,
+                       const void *v1, const void *y2, const void *u2, const void *v2, const aivc_fmap *dst,
+                       const aivc_fmap *dst2, void *stream);
+
 /* MOFNetDecoder post-processing + motion compensation + alpha split
  * (decode.py:729-739, 524-536; optical_flow.py:14-55).  mof: 6 channels (alpha, beta,
  * v_prev xy, v_next xy).  frame_is_p: beta := 1, v_next := 0.
