@@ -25,15 +25,15 @@ from .codec import FrameCodec, latent_dims
 from .gop import generate_gop_struct, FRAME_I
 from .plan import Config
 
-_CODECS = {}
-
-
 def codec_for(model, h, w, device, cfg=None, idx_rate=0.):
+    """FrameCodec of `model` for this frame size, cached ON the model (a cache keyed by id(model) would hand
+    a dead model's codec to a new model that happens to reuse the address)."""
     cfg = cfg or Config()
-    key = (id(model), h, w, str(device), cfg.key(), float(idx_rate))
-    c = _CODECS.get(key)
+    cache = model.__dict__.setdefault('_aivc_b200_codecs', {})
+    key = (h, w, str(device), cfg.key(), float(idx_rate))
+    c = cache.get(key)
     if c is None:
-        c = _CODECS[key] = FrameCodec(model, h, w, device, cfg, idx_rate)
+        c = cache[key] = FrameCodec(model, h, w, device, cfg, idx_rate)
     return c
 
 
@@ -136,3 +136,15 @@ def decode_video(model, video_bytes, device='cuda:0', cfg=None):
         codec = codec_for(model, h, w, torch.device(device), cfg, idx_rate)
         out.append(codec.decode_gop(dict(zip(order, frames)), gop))
     return out, dims, first, last
+
+
+def encode_yuv(model, path_in, gop_name, idx_start=0, idx_end=-1, device='cuda:0', cfg=None, idx_rate=0.):
+    """Planar .yuv file -> AIVC video bitstream bytes, without the reference's PNG detour (yuvio.py)."""
+    from . import yuvio
+    return yuvio.encode_yuv_file(codec_for, model, path_in, gop_name, idx_start, idx_end, device, cfg, idx_rate)
+
+
+def decode_to_yuv(model, video_bytes, path_out, device='cuda:0', cfg=None):
+    """AIVC video bitstream bytes -> planar .yuv file; returns the number of frames written."""
+    from . import yuvio
+    return yuvio.decode_to_yuv_file(decode_video, model, video_bytes, path_out, device, cfg)

@@ -189,3 +189,35 @@ def test_space_to_depth_first_layer_is_the_same_convolution(size):
     out = F.conv2d(s2d, s2d_weights(w16.float()).double())
     assert out.shape == ref.shape
     assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)      # (weights pass through fp32)
+
+
+def test_yuv_file_io_roundtrip_and_gop_schedule(tmp_path):
+    """yuvio: name parser (format_conversion/utils.py:45-50, 69-72), frame layout, pinned staging, the
+    reference's GOP split with a padded last GOP (model_management.py:142-173)."""
+    import torch
+    from aivc_b200 import yuvio
+    assert yuvio.parse_name('/x/y/BlowingBubbles_416x240_50_420.yuv') == (416, 240, 50.0)
+    with pytest.raises(ValueError):
+        yuvio.parse_name('clip.yuv')
+    w, h, n = 18, 10, 5
+    rng = np.random.default_rng(3)
+    frames = [(rng.integers(0, 256, w * h, dtype=np.uint8), rng.integers(0, 256, (w // 2) * (h // 2), dtype=np.uint8),
+               rng.integers(0, 256, (w // 2) * (h // 2), dtype=np.uint8)) for _ in range(n)]
+    path = str(tmp_path / ('clip_%dx%d_30_420.yuv' % (w, h)))
+    with yuvio.YuvWriter(path) as wr:
+        for f in frames:
+            wr.append(f)
+    rd = yuvio.YuvReader(path)
+    assert (len(rd), rd.w, rd.h, rd.fps) == (n, w, h, 30.0) and rd.fb == w * h * 3 // 2
+    for i in (0, 4, 2):
+        for a, b, c in zip(rd.frame(i), frames[i], rd.pinned(i)):
+            assert np.array_equal(a, b) and np.array_equal(c.numpy(), b)
+    with pytest.raises(IndexError):
+        rd.frame(n)
+    assert yuvio.gop_schedule(0, 4, 3) == [(0, 3), (3, 2)] and yuvio.gop_schedule(2, 4, 3) == [(2, 3)]
+    g = rd.gop_frames(3, 3, 4, torch.device('cpu'))           # frames 3, 4 and the padding copy of 4
+    assert np.array_equal(g['frame_1'][0].numpy(), frames[4][0]) and np.array_equal(g['frame_2'][0].numpy(), frames[4][0])
+    assert np.array_equal(g['frame_0'][2].numpy(), frames[3][2])
+    open(str(tmp_path / 'bad_18x10_30_420.yuv'), 'wb').write(b'123')
+    with pytest.raises(ValueError):
+        yuvio.YuvReader(str(tmp_path / 'bad_18x10_30_420.yuv'))
