@@ -76,6 +76,8 @@ _SIGS = {
                                          C.c_void_p]),
     'aivc_fmap_to_i16': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
     'aivc_i16_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+    'aivc_frame_metrics_scratch_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'aivc_frame_metrics': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     'aivc_rc_bound': (C.c_size_t, [C.c_size_t]),
     'aivc_rc_encode_bounds': (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_size_t)]),

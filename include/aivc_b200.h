@@ -223,6 +223,16 @@ int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *d
 int aivc_fmap_to_i16(const aivc_fmap *src, int16_t *dst, void *stream);
 int aivc_i16_to_fmap(const int16_t *src, const aivc_fmap *dst, void *stream);
 
+/* ---- encoder-side metrics --------------------------------------- */
+/* MSE / PSNR over Y, U, V (loss_function.py:415-435, 234) and plane-size-weighted MS-SSIM (loss_function.py:
+ * 438-470; func_util/ms_ssim.py:37-150: five scales, 11x11 Gaussian window, val_range 1) of two frames given
+ * as uint8 4:2:0 planes on the device.  out (device): mse, psnr, ms_ssim, ms_ssim_db.  Deterministic
+ * (fixed-order reductions); agrees with the reference's fp32 evaluation to ~1e-6, not bit for bit. */
+size_t aivc_frame_metrics_scratch_bytes(int h, int w);
+int aivc_frame_metrics(const uint8_t *ya, const uint8_t *ua, const uint8_t *va, const uint8_t *yb,
+                       const uint8_t *ub, const uint8_t *vb, int h, int w, void *scratch,
+                       size_t scratch_bytes, float *out, void *stream);
+
 /* ---- range coder (host; replaces torchac as called at bitstream.py:281,454,482) ------ */
 /* All pointers are HOST memory.  Output capacity must be >= aivc_rc_bound(n). */
 size_t aivc_rc_bound(size_t n_symbols);

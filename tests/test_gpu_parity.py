@@ -282,3 +282,21 @@ def test_yuv_file_to_bitstream_to_yuv_file(dev, tmp_path):
             for a, b in zip(rec['frame_%d' % j], dec.frame(k)):
                 assert np.array_equal(a.cpu().numpy(), b)
             k += 1
+
+
+@pytest.mark.parametrize('case', [0, 1, 2])
+def test_frame_metrics_vs_oracle(case, dev):
+    """aivc_frame_metrics (MSE / PSNR / plane-weighted MS-SSIM on the device) against the oracle pinned to the
+    reference's loss_function classes; tolerance: separable fp32 filtering vs direct 2-D convolution."""
+    from aivc_b200 import metrics
+    from oracle import metrics_ref as M, gen_golden_metrics as Gm
+    seed, h, w = Gm.CASES[case]
+    a, b = Gm.planes(seed, h, w)
+    ref = M.frame_metrics(Gm.as_dic(a), Gm.as_dic(b))
+    to_dev = lambda pl: tuple(torch.from_numpy(np.ascontiguousarray(p).reshape(-1)).to(dev) for p in pl)
+    got = metrics.frame_metrics(to_dev(a), to_dev(b), h, w)
+    assert abs(got['mse'] - ref['mse']) <= 1e-6 * ref['mse'] + 1e-12
+    assert abs(got['psnr'] - ref['psnr']) <= 1e-4
+    assert abs(got['ms_ssim'] - ref['ms_ssim']) <= 2e-5
+    again = metrics.frame_metrics(to_dev(a), to_dev(b), h, w)
+    assert again == got                                    # fixed-order reductions: run-to-run identical

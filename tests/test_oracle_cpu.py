@@ -63,3 +63,16 @@ def test_system_golden_decodes(golden_dir):
             for k in 'yuv':
                 got = (rec[f][k].numpy() * 255).round().astype(np.uint8)
                 assert np.array_equal(got, fx['%s_rec_%s_%s' % (mode, f, k)])
+
+
+def test_metrics_oracle_reproduces_reference_golden(golden_dir):
+    """oracle/metrics_ref.py against the values the reference's own MSELoss / MSSSIMLoss gave for the same
+    seeded planes (oracle/gen_golden_metrics.py): odd sizes, windows shrinking below 11 at the small scales."""
+    import os
+    from oracle import metrics_ref as M, gen_golden_metrics as Gm
+    cases = np.load(os.path.join(golden_dir, 'metrics.npz'))['cases']
+    assert len(cases) == len(Gm.CASES)
+    for seed, h, w, mse, ms in cases:
+        a, b = Gm.planes(int(seed), int(h), int(w))
+        got = M.frame_metrics(Gm.as_dic(a), Gm.as_dic(b))
+        assert abs(got['mse'] - mse) <= 1e-9 and abs(got['ms_ssim'] - ms) <= 2e-6
