@@ -134,3 +134,38 @@ def test_codec_bf16_closed_loop(golden_dir, dev):
             ref = fx['spec_rec_%s_%s' % (f, k)].reshape(-1).astype(np.int32)
             worst = max(worst, int(np.abs(p.cpu().numpy().astype(np.int32) - ref).max()))
     assert worst <= 8, 'bf16 reconstruction deviates by %d levels' % worst
+
+
+@pytest.mark.parametrize('size', [(135, 241), (64, 96), (33, 47)])
+@pytest.mark.parametrize('cin_ref, off', [(9, 0), (6, 3)])
+def test_first_layer_space_to_depth_vs_oracle(size, cin_ref, off, dev):
+    """The bf16 engine's first layer -- 5x5 stride-2 conv + GDN on the 16-channel level-unit pixel buffer,
+    lowered to space-to-depth + 3x3 on the fused conv+GDN kernel -- against the oracle on odd and even sizes
+    (ceil-halving, per-pixel replicate border), for g_a (channels 0..8) and g_a_ref (a slice at offset 3)."""
+    import ctypes as C
+    import aivc_b200.layers as M
+    from aivc_b200 import _lib
+    from aivc_b200.plan import Plan, Buffer, Config
+    from aivc_b200._lib import BF16
+    from oracle import nn_ref as R
+    h, w = size
+    torch.manual_seed(h + cin_ref)
+    m = M.CustomConvLayer(5, cin_ref, 128, non_linearity='gdn', conv_stride=2).eval()
+    levels = torch.randint(0, 256, (1, 9, h, w), generator=torch.Generator().manual_seed(w)).float()
+    with torch.no_grad():
+        ref = R.forward_module(m, levels[:, off:off + cin_ref] / 255.).numpy()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        buf = Buffer(h, w, 16, 2, BF16, dev)
+        fm = buf.view(0, 9)
+        xd = levels.to(dev).contiguous()
+        _lib.check(L.aivc_nchw_to_fmap(xd.data_ptr(), C.byref(fm), _lib.stream_ptr()))
+        plan = Plan(m, h, w, cin_ref, dev, Config(precision='bf16'), src_buf=buf, in_embed=(16, off, 1.0 / 255.0))
+        assert [s.kind for s in plan.stages] == [3, 0] and plan.stages[1].k == 3 and plan.stages[1].src.c == 64
+        plan.run()
+        fo = plan.out_fmap
+        out = torch.empty((1, fo.c, fo.h, fo.w), dtype=torch.float32, device=dev)
+        _lib.check(L.aivc_fmap_to_nchw(C.byref(fo), out.data_ptr(), _lib.stream_ptr()))
+    y = out.cpu().numpy()
+    assert y.shape == ref.shape
+    _check(y, ref, 0.01)
