@@ -99,10 +99,20 @@ struct BitReader {
     BitReader(const uint8_t *i, size_t l) : in(i), len(l) {}
     inline uint32_t get(int n) {          // n <= 32; bits past the end read as zero
         if (n == 0) return 0;
-        while (avail < n) {
-            acc = (acc << 8) | (pos < len ? in[pos] : 0);
-            ++pos;
-            avail += 8;
+        if (avail < n) {                  // refill: four bytes at once while they exist, bytewise at the tail
+            if (avail <= 32 && pos + 4 <= len) {
+                uint32_t w;
+                memcpy(&w, in + pos, 4);
+                acc = (acc << 32) | (uint64_t)__builtin_bswap32(w);
+                pos += 4;
+                avail += 32;
+            } else {
+                while (avail < n) {
+                    acc = (acc << 8) | (pos < len ? in[pos] : 0);
+                    ++pos;
+                    avail += 8;
+                }
+            }
         }
         avail -= n;
         const uint64_t v = acc >> avail;
@@ -268,10 +278,13 @@ int aivc_rc_decode_laplace_win(const float *b, const uint16_t *win, const uint8_
         const uint64_t X = ((uint64_t)d.value - (uint64_t)d.low + 1) << 16;
         uint32_t lo, hi;
         int v;
-        if (X > w[0] * span && !(X > w[7] * span)) {
-            int j = 3;                                   // q = 0 first: cdf(256) <= target < cdf(257)
-            if (!(X > w[3] * span)) { j = 2; while (!(X > w[j] * span)) --j; }
-            else { while (X > w[j + 1] * span) ++j; }
+        // branch-free: how many of the eight window entries lie at or below the target (symbols are close to
+        // random, so a data-dependent walk would mispredict every other symbol)
+        int cnt = 0;
+#pragma GCC unroll 8
+        for (int j = 0; j < 8; ++j) cnt += (X > w[j] * span) ? 1 : 0;
+        if (cnt >= 1 && cnt <= 7) {
+            const int j = cnt - 1;
             v = AIVC_WIN_FIRST + j; lo = w[j]; hi = w[j + 1];
         } else {
             v = laplace_search(b[i], d.target(), &lo, &hi);
