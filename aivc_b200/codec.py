@@ -43,10 +43,18 @@ def _gain_of(net, frame_type):
     return net.gain_P if frame_type == FRAME_P else net.gain_B
 
 
-def _gain_vec(gm, idx_rate, mode):
+def _gain_vec(gm, idx_rate, mode, c):
+    """abs(gain) of `mode` as `c` per-channel floats; a GainMatrix built with scalar_gain=True holds ONE value
+    for all channels (gain_matrix.py:92-120) -- the kernels index the vector by channel, so it is expanded."""
     if hasattr(gm, 'gain_vector'):
-        return gm.gain_vector(idx_rate, mode).reshape(-1)
-    return gm.interpolate_gain_vector(idx_rate, mode=mode).detach().reshape(-1)
+        g = gm.gain_vector(idx_rate, mode).reshape(-1)
+    else:
+        g = gm.interpolate_gain_vector(idx_rate, mode=mode).detach().reshape(-1)
+    if g.numel() == 1:
+        g = g.expand(c)
+    if g.numel() != c:
+        raise ValueError('GainMatrix holds %d gains for a %d-channel latent' % (g.numel(), c))
+    return g.float().contiguous()
 
 
 class CondNetEngine:
@@ -81,8 +89,8 @@ class CondNetEngine:
         self.gains = {}
         for ft in (FRAME_I, FRAME_P, FRAME_B):
             gm = _gain_of(net, ft)
-            self.gains[ft] = (_gain_vec(gm, idx_rate, 'enc').float().to(device).contiguous(),
-                              _gain_vec(gm, idx_rate, 'dec').float().to(device).contiguous())
+            self.gains[ft] = (_gain_vec(gm, idx_rate, 'enc', cy).to(device).contiguous(),
+                              _gain_vec(gm, idx_rate, 'dec', cy).to(device).contiguous())
         n_y, n_z = cy * hy * wy, cz * hz * wz
         self.n_y, self.n_z = n_y, n_z
         dev = dict(device=device)
@@ -102,6 +110,10 @@ class CondNetEngine:
             pin = dict(pin_memory=True)
             self._slots.append(SimpleNamespace(
                 z=torch.empty(self.n_z, dtype=torch.int16, **pin),
+                # decoder: this latent's z on the device.  The hyper-decoder is re-run from it at synthesis
+                # time; re-reading the pinned host copy there would race with the host rewriting the slot
+                # for the next GOP while this GOP's reconstruction is still queued on the stream
+                z_keep=torch.empty(self.n_z, dtype=torch.int16, device=self.device),
                 bounds=torch.empty(self.n_y, dtype=torch.int32, **pin),
                 nz=torch.empty(self.cy, dtype=torch.int32, **pin),
                 b=torch.empty(self.n_y, dtype=torch.float32, **pin), win=None,
@@ -192,7 +204,10 @@ class CondNetEngine:
         (hy, wy), (hz, wz) = self.dims_y, self.dims_z
         if z is None:
             z = entropy.decode_z(self.table, sec_z, self.cz, hz, wz)
+        # the previous user of this pinned slot has been waited for (its event was synchronised by
+        # entropy_finish / encode_finish before the GOP call returned), so the host may rewrite it
         sl.z.copy_(torch.from_numpy(z).reshape(-1))
+        sl.z_keep.copy_(sl.z, non_blocking=True)
         sl.sec_y = sec_y
         self._hyper_from_slot(sl)
         hs_y = self._hs_view()
@@ -210,9 +225,8 @@ class CondNetEngine:
 
     def _hyper_from_slot(self, sl):
         L, st = _lib.lib(), _lib.stream_ptr()
-        self.z_dev.copy_(sl.z, non_blocking=True)
         zf = self.h_s.in_fmap
-        _lib.check(L.aivc_i16_to_fmap(self.z_dev.data_ptr(), C.byref(zf), st))
+        _lib.check(L.aivc_i16_to_fmap(sl.z_keep.data_ptr(), C.byref(zf), st))
         self.h_s.run()
 
     def entropy_finish(self, sl):

@@ -39,7 +39,8 @@ int validate_fmap(const aivc_fmap *m, const char *what) {
     if (m->h <= 0 || m->w <= 0 || m->c <= 0) AIVC_FAIL("%s: empty feature map %dx%dx%d", what, m->h, m->w, m->c);
     if (m->c_off < 0 || m->c_off + m->c > m->c_stride) AIVC_FAIL("%s: channel view [%d,%d) exceeds pixel stride %d", what, m->c_off, m->c_off + m->c, m->c_stride);
     if (m->pad < 0 || m->pitch < m->w + 2 * m->pad || m->rows < m->h + 2 * m->pad) AIVC_FAIL("%s: pitch/rows smaller than padded size", what);
-    if (m->dtype != AIVC_F32 && m->dtype != AIVC_BF16 && m->dtype != AIVC_F16) AIVC_FAIL("%s: unknown dtype %d", what, m->dtype);
+    if (m->dtype != AIVC_F32 && m->dtype != AIVC_BF16 && m->dtype != AIVC_F16 && m->dtype != AIVC_BF16X2) AIVC_FAIL("%s: unknown dtype %d", what, m->dtype);
+    if (m->dtype == AIVC_BF16X2 && ((m->c_stride & 1) || m->c_off + m->c > m->c_stride / 2)) AIVC_FAIL("%s: split-bf16 view [%d,%d) exceeds half the pixel stride %d", what, m->c_off, m->c_off + m->c, m->c_stride);
     return 0;
 }
 

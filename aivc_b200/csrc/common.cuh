@@ -47,11 +47,21 @@ __device__ __forceinline__ size_t fm_index(const FMap &m, int y, int x, int ch) 
     return ((size_t)(y + m.pad) * m.pitch + (x + m.pad)) * m.c_stride + m.c_off + ch;
 }
 
+// Split-bf16 maps (AIVC_BF16X2, the bf16x3 precision mode): a pixel holds c_stride bf16 elements, the first
+// half the leading 8 bits ("hi") of every channel and the second half the next 8 ("lo" = bf16(v - hi));
+// the value is hi + lo (16 significant bits, fp32 exponent range).
+__device__ __forceinline__ void bf16_split(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 __device__ __forceinline__ float fm_load(const FMap &m, int y, int x, int ch) {
     const size_t i = fm_index(m, y, x, ch);
     if (m.dtype == AIVC_F32) return ((const float *)m.data)[i];
     if (m.dtype == AIVC_F16) return __half2float(((const __half *)m.data)[i]);
-    return __bfloat162float(((const __nv_bfloat16 *)m.data)[i]);
+    const __nv_bfloat16 *b = (const __nv_bfloat16 *)m.data;
+    if (m.dtype == AIVC_BF16X2) return __bfloat162float(b[i]) + __bfloat162float(b[i + (m.c_stride >> 1)]);
+    return __bfloat162float(b[i]);
 }
 
 __device__ __forceinline__ void fm_store_raw(const FMap &m, int yp, int xp, int ch, float v) {
@@ -59,7 +69,10 @@ __device__ __forceinline__ void fm_store_raw(const FMap &m, int yp, int xp, int 
     const size_t i = ((size_t)yp * m.pitch + xp) * m.c_stride + m.c_off + ch;
     if (m.dtype == AIVC_F32) ((float *)m.data)[i] = v;
     else if (m.dtype == AIVC_F16) ((__half *)m.data)[i] = __float2half_rn(v);
-    else ((__nv_bfloat16 *)m.data)[i] = __float2bfloat16_rn(v);
+    else if (m.dtype == AIVC_BF16X2) {
+        __nv_bfloat16 *b = (__nv_bfloat16 *)m.data;
+        bf16_split(v, b[i], b[i + (m.c_stride >> 1)]);
+    } else ((__nv_bfloat16 *)m.data)[i] = __float2bfloat16_rn(v);
 }
 
 // store element (y,x,ch) and its replicas in the border (edge pixels own their border copies)

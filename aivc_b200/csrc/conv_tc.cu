@@ -45,6 +45,8 @@ struct TcParams {
     int mh, mw, out_step, mode;                  // mode 0: 3-D map, 1: 5-D map
     int tmem_cols, kg;                           // kg: columns per swizzle atom of the GDN operands
     int nstages, xsq_off;                        // pipeline depth; byte offset of the x^2 operand tile
+    int x3, a_lo, b_lo;                          // split-bf16 operands (AIVC_ENGINE_TC_X3): every (tap, chunk) runs as
+                                                 // hi.Whi, lo.Whi, hi.Wlo; channel coordinates of the lo halves
     uint32_t stage_bytes, a_bytes, b_bytes, item_bytes;
     Phase ph[4];
 };
@@ -72,7 +74,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
     const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x % p.tiles_x;
     const int my0 = tile_y * p.th, mx0 = tile_x * p.tw;
     const int N = p.cout;
-    const int total_it = ph.ntaps * p.kchunks;
+    const int kv = p.x3 ? 3 * p.kchunks : p.kchunks;           // virtual chunks per tap
+    const int total_it = ph.ntaps * kv;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGES; ++s) {
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             if (p.gdn) {
-                const int chunks = N / p.kg;
-                mbar_expect_tx(&bar_gamma, (uint32_t)(N * N * 2));
+                const int chunks = (p.x3 ? 2 : 1) * N / p.kg;           // x3: gamma is [N][hi N | lo N]
+                mbar_expect_tx(&bar_gamma, (uint32_t)(chunks * p.kg * N * 2));
                 for (int c = 0; c < chunks; ++c)
                     tma_load_2d(gam_tile + (size_t)c * N * p.kg * 2, &tmG, &bar_gamma, c * p.kg, 0);
             }
@@ -121,13 +124,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 mbar_expect_tx(&bar_full[s], (uint32_t)n * (p.a_bytes + p.b_bytes));
                 uint8_t *dst = tiles + (size_t)s * p.stage_bytes;
                 for (int g = 0; g < n; ++g, dst += p.item_bytes) {
+                    int ca = kc * BK, cb = kc * BK;
+                    if (p.x3) {                                 // virtual chunk -> (part, real chunk)
+                        const int part = kc / p.kchunks, j = kc - part * p.kchunks;
+                        ca = j * BK + (part == 1 ? p.a_lo : 0);
+                        cb = j * BK + (part == 2 ? p.b_lo : 0);
+                    }
                     if (p.mode == 0)
-                        tma_load_3d(dst, &tmA, &bar_full[s], kc * BK, mx0 + ph.ax[t], my0 + ph.ay[t]);
+                        tma_load_3d(dst, &tmA, &bar_full[s], ca, mx0 + ph.ax[t], my0 + ph.ay[t]);
                     else
-                        tma_load_5d(dst, &tmA, &bar_full[s], kc * BK, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
+                        tma_load_5d(dst, &tmA, &bar_full[s], ca, ph.qx[t], mx0 + ph.ax[t], ph.qy[t],
                                     my0 + ph.ay[t]);
-                    tma_load_3d(dst + p.a_bytes, &tmB, &bar_full[s], kc * BK, 0, ph.widx[t]);
-                    if (++kc == p.kchunks) { kc = 0; ++t; }
+                    tma_load_3d(dst + p.a_bytes, &tmB, &bar_full[s], cb, 0, ph.widx[t]);
+                    if (++kc == kv) { kc = 0; ++t; }
                 }
                 if (++s == NSTAGES) { s = 0; par ^= 1u; }
             }
@@ -161,12 +170,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 mbar_wait(&bar_xsq, 0);
                 tc_fence_after();
                 const int rowb = p.kg * 2;
-                for (int k16 = 0; k16 < N / 16; ++k16) {
-                    const int chunk = (k16 * 16) / p.kg, inner = (k16 * 16) % p.kg;
-                    const uint64_t ad = make_desc(smem_u32(xsq_tile + (size_t)chunk * 128 * rowb) + inner * 2, rowb);
-                    const uint64_t bd = make_desc(smem_u32(gam_tile + (size_t)chunk * N * rowb) + inner * 2, rowb);
-                    umma_bf16(tmem_base + (uint32_t)N, ad, bd, idesc, k16 > 0 ? 1u : 0u);
-                }
+                const int nch = N / p.kg;                      // chunks of one half (hi or lo) of x^2 / gamma
+                for (int part = 0; part < (p.x3 ? 3 : 1); ++part)        // hi.Ghi, lo.Ghi, hi.Glo
+                    for (int k16 = 0; k16 < N / 16; ++k16) {
+                        const int chunk = (k16 * 16) / p.kg, inner = (k16 * 16) % p.kg;
+                        const int ca = chunk + (part == 1 ? nch : 0), cb = chunk + (part == 2 ? nch : 0);
+                        const uint64_t ad = make_desc(smem_u32(xsq_tile + (size_t)ca * 128 * rowb) + inner * 2, rowb);
+                        const uint64_t bd = make_desc(smem_u32(gam_tile + (size_t)cb * N * rowb) + inner * 2, rowb);
+                        umma_bf16(tmem_base + (uint32_t)N, ad, bd, idesc, (part | k16) ? 1u : 0u);
+                    }
                 umma_commit(&bar_norm);
             }
         }
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
         const int oy = my * p.out_step + ph.out_py, ox = mx * p.out_step + ph.out_px;
         const bool valid = (my < p.mh) && (mx < p.mw) && (oy < p.out.h) && (ox < p.out.w);
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, p.act_channels, p.out_scale != nullptr);
+        const EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, p.act_channels, p.out_scale != nullptr, p.x3 != 0);
 
         mbar_wait(&bar_acc, 0);
         tc_fence_after();
@@ -190,13 +202,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
             for (int j0 = 0; j0 < N; j0 += 16) {
                 float v[16];
                 tmem_ld16(tlane + (uint32_t)j0, v);
-                uint32_t w[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float a = v[2 * i] + sbias[j0 + 2 * i], b = v[2 * i + 1] + sbias[j0 + 2 * i + 1];
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(a * a, b * b);
-                    w[i] = *reinterpret_cast<const uint32_t *>(&b2);
+                for (int i = 0; i < 16; ++i) {
+                    const float a = v[i] + sbias[j0 + i];
+                    v[i] = a * a;
                 }
+                uint32_t w[8], wl[8];
+                split16(v, w, wl);                              // (the lo half is only stored in x3 mode)
                 const int chunk = j0 / p.kg, inner = j0 % p.kg;
                 uint8_t *cbase = xsq_tile + (size_t)chunk * 128 * rowb;
 #pragma unroll
@@ -205,6 +217,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                     off ^= ((off >> 7) & ((1u << sw_bits) - 1u)) << 4;
                     *reinterpret_cast<uint4 *>(cbase + off) =
                         make_uint4(w[4 * hsel], w[4 * hsel + 1], w[4 * hsel + 2], w[4 * hsel + 3]);
+                    if (p.x3)
+                        *reinterpret_cast<uint4 *>(cbase + (size_t)(N / p.kg) * 128 * rowb + off) =
+                            make_uint4(wl[4 * hsel], wl[4 * hsel + 1], wl[4 * hsel + 2], wl[4 * hsel + 3]);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -226,8 +241,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 for (int i = 0; i < 16; ++i) {
                     const float x = v[i] + sbias[j0 + i];
                     const float t = nrm[i] + sbeta[j0 + i];
-                    const float rs = rsqrtf(t);                 // MUFU.RSQ: 2^-22 relative, far below bf16
-                    v[i] = (p.gdn == 1) ? x * rs : x * (t * rs);
+                    if (p.x3) {                                 // fp32-faithful mode: IEEE sqrt and division
+                        const float sq = sqrtf(t);
+                        v[i] = (p.gdn == 1) ? x / sq : x * sq;
+                    } else {
+                        const float rs = rsqrtf(t);             // MUFU.RSQ: 2^-22 relative, far below bf16
+                        v[i] = (p.gdn == 1) ? x * rs : x * (t * rs);
+                    }
                 }
                 if (valid) epi_tail16(v, ctx, sscale, oy, ox, j0, interior, out_elem);
             }

@@ -156,7 +156,28 @@ struct VecInfo {
 };
 __device__ __forceinline__ bool fmap_vec_ok(const FMap &m) {
     const int al = (m.dtype == AIVC_F32) ? 4 : 8;
+    if (m.dtype == AIVC_BF16X2 && (m.c_stride >> 1) % 8) return false;      // lo half 16-byte aligned too
     return (m.c_off % al == 0) && (m.c_stride % al == 0) && (((uintptr_t)m.data & 15) == 0);
+}
+
+// 16 floats -> split bf16: hi[8] / lo[8] packed words (see AIVC_BF16X2)
+__device__ __forceinline__ void split16(const float *v, uint32_t *hi, uint32_t *lo) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t *>(&h2);
+        lo[i] = *reinterpret_cast<const uint32_t *>(&l2);
+    }
+}
+__device__ __forceinline__ void add_packed_bf16x8(float *v, const uint4 &t) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[2 * j] += __uint_as_float(w[j] << 16);
+        v[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+    }
 }
 
 __device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, int ch0, int nvalid, float *v) {
@@ -181,6 +202,11 @@ __device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, in
                     v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
                 }
             }
+            if (m.dtype == AIVC_BF16X2) {                      // + lo half
+                const uint4 *pl = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + base + (m.c_stride >> 1));
+                add_packed_bf16x8(v, pl[0]);
+                add_packed_bf16x8(v + 8, pl[1]);
+            }
         }
     } else {
         for (int i = 0; i < 16; ++i) v[i] = (i < nvalid) ? fm_load(m, y, x, ch0 + i) : 0.f;
@@ -200,6 +226,19 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
                         (float *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+        } else if (m.dtype == AIVC_BF16X2) {
+            uint32_t w[8], l[8];
+            split16(v, w, l);
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) {
+                    uint4 *q = reinterpret_cast<uint4 *>(
+                        (__nv_bfloat16 *)m.data + ((size_t)yy * m.pitch + xx) * m.c_stride + m.c_off + ch0);
+                    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    uint4 *ql = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(q) + (m.c_stride >> 1));
+                    ql[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                    ql[1] = make_uint4(l[4], l[5], l[6], l[7]);
                 }
         } else {
             uint32_t w[8];
@@ -228,16 +267,17 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
 // bias and scale are read from shared memory as broadcast float4.
 struct EpiCtx {
     FMap out, res, gate;
-    int post, act_channels, dbg;
+    int post, act_channels;
     bool has_scale, out_vec, res_vec, gate_vec;
+    bool precise;       // bf16x3 mode: IEEE sigmoid / sqrt / division instead of the fast approximations
 };
 
 __device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, const FMap &gate, int post,
-                                           int act_channels, bool has_scale) {
+                                           int act_channels, bool has_scale, bool precise = false) {
     EpiCtx c;
     c.out = out; c.res = res; c.gate = gate; c.post = post; c.act_channels = act_channels;
     c.has_scale = has_scale;
-    c.dbg = 0;
+    c.precise = precise;
     c.out_vec = fmap_vec_ok(out);
     c.res_vec = res.data ? fmap_vec_ok(res) : false;
     c.gate_vec = gate.data ? fmap_vec_ok(gate) : false;
@@ -259,14 +299,15 @@ __device__ __forceinline__ void post_apply16(int post, float *v) {
 }
 
 template <int ACT>
-__device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int j0, int act_channels) {
+__device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int j0, int act_channels,
+                                               bool precise = false) {
     const float4 *b4 = reinterpret_cast<const float4 *>(sbias + j0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 b = b4[q];
         v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
-    if (ACT == AIVC_ACT_SIGMOID && act_channels == 0) {
+    if (ACT == AIVC_ACT_SIGMOID && act_channels == 0 && !precise) {
         // bf16 engine: ex2.approx + rcp.approx (2^-22 relative) instead of expf + IEEE division
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
@@ -288,6 +329,15 @@ __device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const flo
         float4 *q = reinterpret_cast<float4 *>((float *)m.data + elem);
 #pragma unroll
         for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if (m.dtype == AIVC_BF16X2) {
+        uint32_t w[8], l[8];
+        split16(v, w, l);
+        uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem);
+        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        uint4 *ql = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem + (m.c_stride >> 1));
+        ql[0] = make_uint4(l[0], l[1], l[2], l[3]);
+        ql[1] = make_uint4(l[4], l[5], l[6], l[7]);
     } else {
         uint32_t w[8];
 #pragma unroll
@@ -347,7 +397,6 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
             v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
         }
     }
-    if (c.dbg & 128) { if (v[0] == 123.456f) store16_at(c.out, out_elem + j0, v); return; }
     if (interior && c.out_vec) store16_at(c.out, out_elem + j0, v);
     else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
 }
@@ -383,11 +432,8 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbia
             if (j0 + 16 < N) fetch16(c.gate, gate_elem, j0 + 16, gn);
         }
         float v[16];
-        if (c.dbg & 256) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (float)(j0 + i);
-        } else tmem_ld16(taddr + (uint32_t)j0, v);
-        epi_bias_act16<ACT>(v, sbias, j0, c.act_channels);
+        tmem_ld16(taddr + (uint32_t)j0, v);
+        epi_bias_act16<ACT>(v, sbias, j0, c.act_channels, c.precise);
         if (valid) epi_tail16(v, c, sscale, oy, ox, j0, interior, out_elem, pipe_res ? rb : nullptr, pipe_gate ? gb : nullptr);
     }
 }

@@ -28,8 +28,13 @@ extern "C" {
 
 /* ---- data types / enums ------------------------------------------------------------ */
 enum { AIVC_F32 = 0, AIVC_BF16 = 1,
-       AIVC_F16 = 2 /* only the GEMM form of the output transposed conv (kind 2 input): pixel-domain partial
-                     * sums need the 11-bit mantissa */ };
+       AIVC_F16 = 2, /* only the GEMM form of the output transposed conv (kind 2 input): pixel-domain partial
+                      * sums need the 11-bit mantissa */
+       AIVC_BF16X2 = 3 /* split bf16 (precision mode bf16x3): a pixel holds c_stride bf16 elements, element
+                        * c_off + ch is the leading 8 bits ("hi") of channel ch and element
+                        * c_stride/2 + c_off + ch the next 8 ("lo" = bf16(v - hi)); value = hi + lo.
+                        * A tensor-core stage reads both halves as K-major operands and issues
+                        * hi.Whi + lo.Whi + hi.Wlo, which restores fp32-grade products (2^-17) on tcgen05. */ };
 
 /* activation applied right after bias (custom_conv_layers.py:155-177, attention.py:82) */
 enum {

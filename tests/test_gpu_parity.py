@@ -210,93 +210,3 @@ def test_closed_loop_odd_and_reference_sizes(size, dev):
         assert len(bts[f]) > 16
         for a, b in zip(rec[f], dec[f]):
             assert torch.equal(a, b)
-
-
-def test_gop_forward_contract_and_video_roundtrip(golden_dir, dev, tmp_path):
-    """FullNet.GOP_forward with the reference's model_input dict (model_management.py:307-317):
-    net_out keys, the GOP file it leaves behind, and decode_video of the assembled .bin."""
-    from aivc_b200 import models, gop as G, container, adapter
-    from aivc_b200.plan import Config
-    fx = np.load(os.path.join(golden_dir, 'system_80x112.npz'))
-    h, w = int(fx['H']), int(fx['W'])
-    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
-    gop = G.generate_gop_struct('1_GOP_2')
-    raw = {}
-    for t in range(3):
-        raw['frame_%d' % t] = {}
-        for k in 'yuv':
-            a = fx['src_frame_%d_%s' % (t, k)].astype(np.float32) / 255.
-            raw['frame_%d' % t][k] = torch.from_numpy(a).reshape(1, 1, *a.shape[-2:]).to(dev)
-    d = str(tmp_path) + '/bs/'
-    model_input = {'GOP_struct': gop, 'GOP_struct_name': '1_GOP_2', 'raw_frames': raw, 'idx_rate': 0.,
-                   'index_GOP_in_video': 0, 'generate_bitstream': True, 'real_idx_first_frame': 0,
-                   'bitstream_dir': d, 'flag_bitstream_debug': False}
-    out = adapter.gop_forward(net, model_input, cfg=Config(precision='fp32'))
-    for f in gop:
-        for key in ('x_hat', 'alpha', 'beta', 'warping', 'code', 'mode_rate_y', 'mode_rate_z', 'codec_rate_y',
-                    'codec_rate_z'):
-            assert key in out[f], key
-        for k in 'yuv':
-            got = (out[f]['x_hat'][k].cpu().numpy() * 255).round().astype(np.uint8).reshape(-1)
-            assert np.array_equal(got, fx['spec_rec_%s_%s' % (f, k)].reshape(-1))     # fp32 engine == oracle
-    gbytes = open(d + '0g', 'rb').read()
-    name, rate, frames = container.unpack_gop(gbytes)
-    assert name == '1_GOP_2' and [bytes(b) for b in frames] == [fx['spec_bytes_frame_%d' % i].tobytes() for i in range(3)]
-    # the same content through the video container and back
-    from aivc_b200.codec import latent_dims
-    dy, dz = latent_dims(h, w)
-    video = container.pack_video((h, w), dy, dz, [gbytes], 0, 2)
-    dec, dims, first, last = adapter.decode_video(net, video, dev, Config(precision='fp32'))
-    assert dims['x'] == (h, w) and (first, last) == (0, 2)
-    for f in gop:
-        for k, p in zip('yuv', dec[0][f]):
-            assert np.array_equal(p.cpu().numpy(), fx['spec_rec_%s_%s' % (f, k)].reshape(-1))
-
-
-def test_yuv_file_to_bitstream_to_yuv_file(dev, tmp_path):
-    """Direct .yuv path: 4 frames, GOP of 3 -> two GOPs, the second padded; the
-    decoded file holds exactly the encoder's reconstructions of the 4 real frames."""
-    from aivc_b200 import models, adapter, yuvio, gop as G
-    from aivc_b200.plan import Config
-    w, h = 64, 48
-    rng = np.random.default_rng(9)
-    path = str(tmp_path / ('clip_%dx%d_25_420.yuv' % (w, h)))
-    with yuvio.YuvWriter(path) as wr:
-        for _ in range(4):
-            wr.append((rng.integers(0, 256, w * h, dtype=np.uint8), rng.integers(0, 256, w * h // 4, dtype=np.uint8),
-                       rng.integers(0, 256, w * h // 4, dtype=np.uint8)))
-    net = models.build_standin(seed=3, C=32, Cy=16, Cz=16, Csc=16)
-    cfg = Config(precision='fp32')
-    video = adapter.encode_yuv(net, path, '1_GOP_2', device=dev, cfg=cfg)
-    out = str(tmp_path / 'dec_64x48_25_420.yuv')
-    assert adapter.decode_to_yuv(net, video, out, device=dev, cfg=cfg) == 4
-    # reference: the same GOPs through encode_gop directly
-    rd, dec = yuvio.YuvReader(path), yuvio.YuvReader(out)
-    assert len(dec) == 4
-    codec = adapter.codec_for(net, h, w, dev, cfg)
-    gop = G.generate_gop_struct('1_GOP_2')
-    k = 0
-    for first, keep in yuvio.gop_schedule(0, 3, 3):
-        _, rec = codec.encode_gop(rd.gop_frames(first, 3, 3, dev), gop)
-        for j in range(keep):
-            for a, b in zip(rec['frame_%d' % j], dec.frame(k)):
-                assert np.array_equal(a.cpu().numpy(), b)
-            k += 1
-
-
-@pytest.mark.parametrize('case', [0, 1, 2])
-def test_frame_metrics_vs_oracle(case, dev):
-    """aivc_frame_metrics (MSE / PSNR / plane-weighted MS-SSIM on the device) against the oracle pinned to the
-    reference's loss_function classes; tolerance: separable fp32 filtering vs direct 2-D convolution."""
-    from aivc_b200 import metrics
-    from oracle import metrics_ref as M, gen_golden_metrics as Gm
-    seed, h, w = Gm.CASES[case]
-    a, b = Gm.planes(seed, h, w)
-    ref = M.frame_metrics(Gm.as_dic(a), Gm.as_dic(b))
-    to_dev = lambda pl: tuple(torch.from_numpy(np.ascontiguousarray(p).reshape(-1)).to(dev) for p in pl)
-    got = metrics.frame_metrics(to_dev(a), to_dev(b), h, w)
-    assert abs(got['mse'] - ref['mse']) <= 1e-6 * ref['mse'] + 1e-12
-    assert abs(got['psnr'] - ref['psnr']) <= 1e-4
-    assert abs(got['ms_ssim'] - ref['ms_ssim']) <= 2e-5
-    again = metrics.frame_metrics(to_dev(a), to_dev(b), h, w)
-    assert again == got                                    # fixed-order reductions: run-to-run identical
