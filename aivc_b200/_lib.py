@@ -10,10 +10,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AIVC_B200_LIB: alternative build of the same ABI (A/B timing of kernel changes on one box)
 LIB_PATH = os.environ.get('AIVC_B200_LIB') or os.path.join(_HERE, 'libaivc_b200.so')
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, BF16X2 = 0, 1, 2, 3     # BF16X2: split bf16 (hi | lo halves of a pixel), see aivc_b200.h
 ACT = {'no': 0, 'none': 0, 'leaky_relu': 1, 'relu': 2, 'sigmoid': 3, 'gdn': 4, 'gdn_inverse': 5}
 POST = {'none': 0, 'leaky_relu': 1, 'relu': 2, 'round_clamp': 3}
-ENGINE_SIMT, ENGINE_TC = 0, 1
+ENGINE_SIMT, ENGINE_TC, ENGINE_TC_X3 = 0, 1, 2
 
 
 class FMap(C.Structure):

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, entropy
-from ._lib import F32, BF16
+from ._lib import F32, BF16, BF16X2
 from .gop import FRAME_I, FRAME_P, FRAME_B, coding_order
 from .plan import Plan, Buffer, Config
 
@@ -67,7 +67,7 @@ class CondNetEngine:
         (hy, wy), (hz, wz) = latent_dims(h, w)
         self.dims_y, self.dims_z = (hy, wy), (hz, wz)
         exact = cfg.hyper_cfg()                    # hyperprior engine ('fp32' keeps sigma/mu exact)
-        tc = cfg.precision == 'bf16'
+        tc = cfg.tc
         embed = (lambda off: (in_buf.c, off, (1.0 / 255.0) if levels else 1.0)) if tc else (lambda off: None)
         self.g_s = Plan(net.g_s, hy, wy, cy + csc, device, cfg, pad_cout=16 if tc else 0)
         self.gs_in = self.g_s.src.buf
@@ -128,8 +128,7 @@ class CondNetEngine:
         if use and self.has_ref:
             self.g_a_ref.run()
         else:   # zeros (decode.py:891-892), border included
-            full = self.gs_in.t.view(self.gs_in.rows, self.gs_in.pitch, self.gs_in.c)
-            full[:, :, self.cy:].zero_()
+            self.gs_in.zero_channels(self.cy, self.gs_in.c)
 
     # ---------------------------------------------------------------- encoder
     def encode_launch(self, sl, frame_type, use_shortcut, first_of_i_frame=False):
@@ -267,14 +266,14 @@ class FrameCodec:
         self.device = torch.device(device)
         self.cfg = cfg or Config()
         self.idx_rate = idx_rate
-        # bf16 engine: pixel inputs live in 16-channel bf16 pixels (zero padded) holding 8-bit LEVEL
-        # units -- exact in bf16 -- with a 2-pixel replicate border for the 5x5 first conv; the
+        # tensor-core engines: pixel inputs live in 16-channel (split-)bf16 pixels (zero padded) holding 8-bit
+        # LEVEL units -- exact in bf16 -- with a 2-pixel replicate border for the 5x5 first conv; the
         # 1/255 is folded into the first-layer weights.  fp32 engine: plain [0,1] fp32 pixels.
-        self.levels = self.cfg.precision == 'bf16'
+        self.levels = self.cfg.tc
         with torch.cuda.device(self.device):
             if self.levels:
-                self.mof_in = Buffer(h, w, 16, 2, BF16, self.device)
-                self.codec_in = Buffer(h, w, 16, 2, BF16, self.device)
+                self.mof_in = Buffer(h, w, 16, 2, self.cfg.act_dtype, self.device)
+                self.codec_in = Buffer(h, w, 16, 2, self.cfg.act_dtype, self.device)
             else:
                 self.mof_in = Buffer(h, w, 9, 0, F32, self.device)
                 self.codec_in = Buffer(h, w, 6, 0, F32, self.device)
@@ -314,11 +313,10 @@ class FrameCodec:
                                                  _lib.stream_ptr()))
 
     def _fusable(self, *frames):
-        return self.levels and all(f is None or f[0].dtype == torch.uint8 for f in frames)
+        return self.cfg.precision == 'bf16' and all(f is None or f[0].dtype == torch.uint8 for f in frames)
 
     def _zero_pred(self):
-        full = self.codec_in.t.view(self.codec_in.rows, self.codec_in.pitch, self.codec_in.c)
-        full[:, :, 3:6].zero_()
+        self.codec_in.zero_channels(3, 6)
 
     def _motion(self, frame_type):
         L = _lib.lib()

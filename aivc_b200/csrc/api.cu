@@ -80,7 +80,7 @@ const char *aivc_last_error(void) { return g_err; }
 
 int aivc_conv2d_fused(const aivc_conv_op *op, void *stream) {
     if (validate_conv(op)) return 1;
-    if (op->kind < 2 && op->engine != AIVC_ENGINE_SIMT && op->engine != AIVC_ENGINE_TC) AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
+    if (op->kind < 2 && op->engine != AIVC_ENGINE_SIMT && op->engine != AIVC_ENGINE_TC && op->engine != AIVC_ENGINE_TC_X3) AIVC_FAIL("conv2d_fused: unknown engine %d", op->engine);
     StageRec r;
     if (g_prof_on) {
         AIVC_CHECK_CUDA(cudaEventCreate(&r.a));
@@ -135,7 +135,7 @@ int aivc_profile_read(double *out) {
         AIVC_CHECK_CUDA(cudaEventSynchronize(r.b));
         float ms = 0.f;
         AIVC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
-        const int o = r.engine == AIVC_ENGINE_TC ? 0 : 3;
+        const int o = r.engine != AIVC_ENGINE_SIMT ? 0 : 3;
         out[o] += ms; out[o + 1] += r.flops; out[o + 2] += 1.0;
     }
     return 0;
@@ -153,6 +153,31 @@ int aivc_profile_read_classes(double *out, int n) {
     }
     return 0;
 }
+
+}  // extern "C"
+
+#include <mutex>
+namespace tcgen {
+int smem_attr_once(const void *kernel, int bytes) {
+    struct Entry { const void *k; unsigned devmask; };
+    static Entry tab[64];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    AIVC_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    Entry *e = nullptr;
+    for (int i = 0; i < n; ++i)
+        if (tab[i].k == kernel) { e = &tab[i]; break; }
+    if (e && ((e->devmask >> dev) & 1u)) return 0;
+    AIVC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (!e && n < 64) { e = &tab[n++]; e->k = kernel; e->devmask = 0; }
+    if (e && dev < 32) e->devmask |= 1u << dev;
+    return 0;
+}
+}  // namespace tcgen
+
+extern "C" {
 
 struct Lanes { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 static Lanes g_lanes[16];

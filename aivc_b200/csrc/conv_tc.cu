@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
     uint8_t *tiles = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int NSTAGES = p.nstages;
     uint8_t *xsq_tile = tiles + p.xsq_off;            // [chunks][128][kg] bf16; may alias the (drained) stage ring
-    uint8_t *gam_tile = tiles + (size_t)NSTAGES * p.stage_bytes + (p.xsq_off ? 128 * p.cout * 2 : 0);   // [chunks][N][kg]
+    uint8_t *gam_tile = tiles + (size_t)NSTAGES * p.stage_bytes + (p.xsq_off ? 128 * p.cout * 2 * (p.x3 ? 2 : 1) : 0);   // [chunks][N][kg]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Phase &ph = p.ph[blockIdx.z];
@@ -280,8 +280,7 @@ void pick_tile(int mh, int mw, int *tw, int *th) {
 template <int BK>
 int launch_bk(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &g, const TcParams &p, dim3 grid,
               size_t smem, cudaStream_t st) {
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024));
+    if (smem_attr_once((const void *)conv_tc_kernel<BK>, 220 * 1024)) return 1;
     AIVC_CHECK_CUDA(launch_pdl(conv_tc_kernel<BK>, grid, dim3(NTHREADS), smem, st, a, b, g, p));
     AIVC_CHECK_LAUNCH("conv_tc_kernel");
     return 0;
@@ -294,22 +293,21 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st);
 int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st);
 
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
-    {
-        const int r = conv_tc1_run(op, st);                  // persistent 1x1 kernel
+    if (op->engine != AIVC_ENGINE_TC_X3) {                   // (split-bf16 operands: 3x3 persistent kernel or generic)
+        int r = conv_tc1_run(op, st);                        // persistent 1x1 kernel
+        if (r >= 0) return r;
+        r = tconv_tc3_run(op, st);                           // persistent transposed 3x3 kernel
         if (r >= 0) return r;
     }
     {
-        const int r = tconv_tc3_run(op, st);                 // persistent transposed 3x3 kernel
-        if (r >= 0) return r;
-    }
-    static const bool no_tc3 = getenv("AIVC_NO_TC3") != nullptr;     // A/B switch for profiling
-    if (!no_tc3) {
-        const int r = conv_tc3_run(op, st);
+        const int r = conv_tc3_run(op, st);                  // persistent 3x3 kernels
         if (r >= 0) return r;
     }
     g_aivc_kernel_class = AIVC_KC_TC_GENERIC;
     const int k = op->k, cin = op->in.c, cout = op->out.c;
-    if (op->in.dtype != AIVC_BF16) AIVC_FAIL("conv_tc: input feature map must be bf16");
+    const bool x3 = op->engine == AIVC_ENGINE_TC_X3;
+    if (x3 ? op->in.dtype != AIVC_BF16X2 : op->in.dtype != AIVC_BF16)
+        AIVC_FAIL("conv_tc: input feature map must be %s", x3 ? "split bf16 (engine TC_X3)" : "bf16");
     if (cin % 16 || cout % 16 || cout > 256) AIVC_FAIL("conv_tc: cin %d / cout %d not tileable", cin, cout);
     if (k * k > MAX_TAPS) AIVC_FAIL("conv_tc: kernel size %d unsupported", k);
     if (op->in.c_off % 8 || op->in.c_stride % 8) AIVC_FAIL("conv_tc: input channel view must be 16-byte aligned");
@@ -328,6 +326,8 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
     p.bias = op->bias; p.gdn_beta = op->gdn_beta; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / BK;
     p.act = gdn ? AIVC_ACT_NONE : op->act; p.post = op->post; p.act_channels = op->act_channels; p.gdn = gdn;
+    p.x3 = x3 ? 1 : 0; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
+    if (x3 && (p.a_lo % 8)) AIVC_FAIL("conv_tc: split-bf16 input needs 16-byte aligned halves");
     p.kg = cout < 64 ? cout : 64;
     int need_cols = gdn ? 2 * cout : cout;
     p.tmem_cols = 32;
@@ -339,6 +339,8 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
 
     const aivc_fmap &in = op->in;
     const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
+    // channel extent of the activation map: a split-bf16 view also reaches its lo half at + c_stride / 2
+    const int cin_ext = x3 ? p.a_lo + cin : cin;
     CUtensorMap tmA, tmB, tmG;
     memset(&tmG, 0, sizeof(tmG));
     int nphase = 1;
@@ -359,7 +361,7 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
                     ph.ay[t] = (signed char)(ky - half + in.pad);
                     ph.widx[t] = (unsigned char)t;
                 }
-            cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
+            cuuint64_t dims[3] = {(cuuint64_t)cin_ext, (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
             cuuint64_t strides[2] = {pix_b, row_b};
             cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th};
             if (encode_map(&tmA, base, 3, dims, strides, box, rowb, "A/3d")) return 1;
@@ -374,7 +376,7 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
                     ph.ay[t] = (signed char)(ey >> 1); ph.qy[t] = (unsigned char)(ey & 1);
                     ph.widx[t] = (unsigned char)t;
                 }
-            cuuint64_t dims[5] = {(cuuint64_t)cin, 2, (cuuint64_t)(in.pitch / 2), 2, (cuuint64_t)(in.rows / 2)};
+            cuuint64_t dims[5] = {(cuuint64_t)cin_ext, 2, (cuuint64_t)(in.pitch / 2), 2, (cuuint64_t)(in.rows / 2)};
             cuuint64_t strides[4] = {pix_b, 2 * pix_b, row_b, 2 * row_b};
             cuuint32_t box[5] = {(cuuint32_t)BK, 1, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th};
             if (encode_map(&tmA, base, 5, dims, strides, box, rowb, "A/5d")) return 1;
@@ -403,7 +405,7 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
                 ph.ntaps = n;
             }
         void *base = (char *)in.data + ((size_t)in.pad * in.pitch + in.pad) * pix_b + (size_t)in.c_off * 2;
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
+        cuuint64_t dims[3] = {(cuuint64_t)cin_ext, (cuuint64_t)in.w, (cuuint64_t)in.h};
         cuuint64_t strides[2] = {pix_b, row_b};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th};
         if (encode_map(&tmA, base, 3, dims, strides, box, rowb, "A/tconv")) return 1;
@@ -411,18 +413,19 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
     p.tiles_x = ceil_div(p.mw, p.tw);
     const int tiles_y = ceil_div(p.mh, p.th);
     {
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(k * k)};
-        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+        const int wcin = x3 ? 2 * cin : cin;                   // x3: [tap][cout][hi cin | lo cin]
+        cuuint64_t dims[3] = {(cuuint64_t)wcin, (cuuint64_t)cout, (cuuint64_t)(k * k)};
+        cuuint64_t strides[2] = {(cuuint64_t)wcin * 2, (cuuint64_t)wcin * cout * 2};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)cout, 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, rowb, "B")) return 1;
     }
     // Pipeline depth.  Two CTAs per SM (<= ~110 KB each) let one CTA's epilogue hide behind the
     // other's main loop; grids that cannot fill the chip twice get one deep pipeline instead.
     const int nctas = p.tiles_x * tiles_y * nphase;
-    const size_t gam_bytes = gdn ? (size_t)cout * cout * 2 : 0;
-    const size_t xsq_bytes = gdn ? (size_t)128 * cout * 2 : 0;
-    static const bool deep = getenv("AIVC_TC_DEEP") != nullptr;      // experiment switch
-    const size_t budget = (deep && nctas <= 148 * 3 / 2) ? 200 * 1024 : 110 * 1024;   // default: two CTAs per SM
+    const size_t gam_bytes = gdn ? (size_t)cout * cout * 2 * (x3 ? 2 : 1) : 0;
+    const size_t xsq_bytes = gdn ? (size_t)128 * cout * 2 * (x3 ? 2 : 1) : 0;
+    (void)nctas;
+    const size_t budget = (x3 && gdn) ? 200 * 1024 : 110 * 1024;   // default: two CTAs per SM
     int nst = (int)((budget - 1024 - gam_bytes) / p.stage_bytes);
     if (nst > MAX_STAGES) nst = MAX_STAGES;
     if (BK == 64 && nst > 3 && budget < 150 * 1024) nst = 3;   // measured: deeper 16 KB-stage rings only add L2 pressure
@@ -435,8 +438,9 @@ int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
         smem += xsq_bytes;
     }
     if (gdn) {
-        cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};
-        cuuint64_t strides[1] = {(cuuint64_t)cout * 2};
+        const int gk = x3 ? 2 * cout : cout;                   // x3: gamma rows are [hi | lo]
+        cuuint64_t dims[2] = {(cuuint64_t)gk, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)gk * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.kg, (cuuint32_t)cout};
         if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, p.kg * 2, "gamma")) return 1;
     }

@@ -269,8 +269,6 @@ static void pick_tile1(int mh, int mw, int *tw, int *th) {      // 128-pixel til
 
 // Returns -1 when the stage does not fit this kernel (caller falls through to the generic one).
 int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
-    static const bool off = getenv("AIVC_NO_TC1") != nullptr;             // A/B switch
-    if (off) return -1;
     const int cin = op->in.c, cout = op->out.c;
     if (op->kind != 0 || op->k != 1 || (op->stride != 1 && op->stride != 2)) return -1;
     if (op->stride == 2 && ((op->in.pitch & 1) || (op->in.rows & 1))) return -1;
@@ -340,7 +338,7 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st) {
         AIVC_CHECK_CUDA(cudaGetDevice(&dev));
         AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024 + 512));
+    if (smem_attr_once((const void *)conv1x1_tc_kernel, 225 * 1024 + 512)) return 1;
     g_aivc_kernel_class = AIVC_KC_TC1;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     AIVC_CHECK_CUDA(launch_pdl(conv1x1_tc_kernel, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, tmG, tmR, tmO, p));

@@ -1,6 +1,5 @@
 // Persistent tcgen05 kernels built around ONE shared activation patch per tile:
 //   conv3x3_tc_kernel<SUB,RES>   3x3 stride-1 conv (+ residual)            -- this header
-//   conv3x3_tc_pair_kernel       the same on cta_group::2 CTA pairs (opt-in: measured slower)
 //   conv3x3_tc_gdn_kernel        3x3 stride-1 conv + GDN / IGDN, norm GEMM with its A operand in TMEM
 //   tconv3x3_tc_kernel           transposed 3x3 stride-2 conv, four output phases per patch
 //
@@ -64,9 +63,19 @@ struct Tc3Params {
     uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
     int tma_store;                    // epilogue stores through smem + TMA (bf16, 32-channel multiples)
-    long long *ts;                    // AIVC_TC3_TS: clock64 timeline of CTA 0 (debug)
-    int dbg;                          // AIVC_TC3_DBG bits: timing experiments only (wrong results)
+    int x3, kv, a_lo, b_lo;           // split-bf16 operands (AIVC_ENGINE_TC_X3): kv = 3 * kchunks virtual chunks
+                                      // (hi.Whi, lo.Whi, hi.Wlo); channel coordinates of the lo halves
 };
+
+// virtual chunk -> channel coordinates of the activation patch and of the weight slice
+__device__ __forceinline__ void chunk_coords(const Tc3Params &p, int kc, int &ca, int &cb) {
+    ca = cb = kc * 64;
+    if (p.x3) {
+        const int part = kc / p.kchunks, j = kc - part * p.kchunks;
+        ca = j * 64 + (part == 1 ? p.a_lo : 0);
+        cb = j * 64 + (part == 2 ? p.b_lo : 0);
+    }
+}
 
 // 16 channels of this thread's pixel as packed bf16 (two 16-byte loads)
 __device__ __forceinline__ void ldg_bf16x16(const __nv_bfloat16 *ptr, uint4 &r0, uint4 &r1) {
@@ -147,15 +156,11 @@ __device__ __forceinline__ void chunk32_to_stage(const Tc3Params &p, uint32_t ta
     }
 }
 
-// PAIR: the CTA is one half of a cta_group::2 pair -- unit u of the loop is the pair's u-th pair of tiles,
-// this CTA takes tile 2u + rank, and the accumulator is released with one (possibly remote) arrive per
-// warp on the LEADER CTA's barrier (`acc_empty_rem`: shared::cluster addresses of the two barriers).
-template <int SUB, int ACT, bool RES, bool PAIR>
+template <int SUB, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
                                               const float *sbias, const float *sscale, uint64_t *acc_full,
                                               uint64_t *acc_empty, uint32_t tmem_base, int warp, int lane,
-                                              int first, int stride, int nunits, int rank = 0,
-                                              uint32_t acc_empty_rem0 = 0, uint32_t acc_empty_rem1 = 0) {
+                                              int first, int stride, int nunits) {
     constexpr int TILE_H = Cfg<SUB>::TILE_H;
     const int quarter = warp & 3, team = warp >> 2, j = team >> 1, h = team & 1;
     const int row = quarter * 32 + lane;
@@ -168,17 +173,17 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
     // (about 1 us under load) never sits on the epilogue's critical path
     // (RES kernels are only launched with TMA stores and a residual the host found prefetchable)
     constexpr bool res_fast = RES;
-    EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr);
+    EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr, p.x3 != 0);
     uint8_t *my_stage = stage + team * STAGE_BYTES;
     uint32_t it = 0;
     bool store_pending = false;
     for (int u = first; u < nunits; u += stride, ++it) {
         const uint32_t buf = it & 1u;
-        const int tile = PAIR ? 2 * u + rank : u / p.nsplit;
-        const int n0 = PAIR ? 0 : (u - tile * p.nsplit) * N;
+        const int tile = u / p.nsplit;
+        const int n0 = (u - tile * p.nsplit) * N;
         const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
         const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
-        const bool valid = (oy < p.out.h) && (ox < p.out.w);      // (a pair's odd tile past the end: all rows invalid)
+        const bool valid = (oy < p.out.h) && (ox < p.out.w);
         const bool use_res = res_fast && valid;
         ctx.out.c_off = p.out.c_off + n0;
         const __nv_bfloat16 *res_px = use_res ? (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0) : nullptr;
@@ -194,7 +199,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
         mbar_wait(&acc_full[buf], (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(128 * SUB) + (uint32_t)(j * 128);
-        if (c_lo < N && !(p.dbg & 2)) {
+        if (c_lo < N) {
             if (p.tma_store) {
                 const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
                 for (int ch0 = c_lo; ch0 < c_hi; ch0 += 32) {
@@ -222,14 +227,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
             }
         }
         tc_fence_before();
-        if (PAIR) {
-            __syncwarp();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(buf ? acc_empty_rem1 : acc_empty_rem0)
-                             : "memory");
-        } else {
-            mbar_arrive(&acc_empty[buf]);
-        }
+        mbar_arrive(&acc_empty[buf]);
     }
     if (store_pending && leader) tma_store_wait_read();        // smem must outlive the last store's read
 }
@@ -253,8 +251,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.ncta;
-    const bool tsw = p.ts && blockIdx.x == 0 && tid == 0;
-    if (tsw) p.ts[0] = clock64();
 
     if (tid == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -269,7 +265,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tsw) p.ts[1] = clock64();
     pdl_launch_dependents();
     stage_vec(sbias, p.bias, p.cout, 0.f, tid, NTHREADS);     // weights/bias never depend on the prior grid
     stage_vec(sscale, p.out_scale, p.cout, 1.f, tid, NTHREADS);
@@ -277,9 +272,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    if (tsw) p.ts[2] = clock64();
     pdl_wait_prior_grid();                                    // activations / residuals below do
-    if (tsw) p.ts[3] = clock64();
 
     if (warp == K::TMA_WARP) {
         // ===================== TMA producer =====================
@@ -290,25 +283,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
                 const int tile = item / p.nsplit, n0 = (item - tile * p.nsplit) * N;
                 const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < p.kv; ++kc) {
+                    int ca, cb;
+                    chunk_coords(p, kc, ca, cb);
                     mbar_wait(&a_empty[sa], pa ^ 1u);
-                    if (p.dbg & 8) mbar_arrive(&a_full[sa]);
-                    else {
-                        mbar_expect_tx(&a_full[sa], PATCH_BYTES);
-                        tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], kc * 64, x0 - 1 + p.in_pad,
-                                    y0 - 1 + p.in_pad);
-                    }
+                    mbar_expect_tx(&a_full[sa], PATCH_BYTES);
+                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], ca, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
                     for (int ky = 0; ky < 3; ++ky) {
                         mbar_wait(&g_empty[sg], pg ^ 1u);
-                        if (p.dbg & 16) mbar_arrive(&g_full[sg]);
-                        else {
-                            mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
-                            uint8_t *dst = g_ring + sg * g_slot;
+                        mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
+                        uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx)
-                                tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], kc * 64, n0, ky * 3 + kx);
-                        }
+                        for (int kx = 0; kx < 3; ++kx)
+                            tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], cb, n0, ky * 3 + kx);
                         if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                     }
                 }
@@ -330,14 +318,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * (uint32_t)(128 * SUB);
                 uint32_t accum = 0;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < p.kv; ++kc) {
                     mbar_wait(&a_full[sa], pa);
                     const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
                     for (int ky = 0; ky < 3; ++ky) {
                         mbar_wait(&g_full[sg], pg);
                         tc_fence_after();
                         const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
-                        if (!(p.dbg & 4)) {
+                        {
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
                                 const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
@@ -366,214 +354,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ===================== epilogue (warps 0 .. 8 SUB - 1) =====================
         switch (p.act) {
-            case AIVC_ACT_LEAKY: epilogue_team<SUB, AIVC_ACT_LEAKY, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
-            case AIVC_ACT_RELU: epilogue_team<SUB, AIVC_ACT_RELU, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
-            case AIVC_ACT_SIGMOID: epilogue_team<SUB, AIVC_ACT_SIGMOID, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
-            default: epilogue_team<SUB, AIVC_ACT_NONE, RES, false>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            case AIVC_ACT_LEAKY: epilogue_team<SUB, AIVC_ACT_LEAKY, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            case AIVC_ACT_RELU: epilogue_team<SUB, AIVC_ACT_RELU, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            case AIVC_ACT_SIGMOID: epilogue_team<SUB, AIVC_ACT_SIGMOID, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
+            default: epilogue_team<SUB, AIVC_ACT_NONE, RES>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, blockIdx.x, gridDim.x, p.nitems); break;
         }
     }
 
-    if (tsw) p.ts[4] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (tsw) p.ts[5] = clock64();
     if (warp == K::MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS)
                      : "memory");
     }
-    if (tsw) p.ts[6] = clock64();
 }
 
 template <int SUB, bool RES>
 int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const Tc3Params &p, int grid,
                size_t smem, cudaStream_t st) {
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<SUB, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024));
+    if (smem_attr_once((const void *)conv3x3_tc_kernel<SUB, RES>, 220 * 1024)) return 1;
     AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_kernel<SUB, RES>, dim3(grid), dim3(Cfg<SUB>::NTHREADS), smem, st, a, b, o, p));
     AIVC_CHECK_LAUNCH("conv3x3_tc_kernel");
-    return 0;
-}
-
-// =====================================================================================================
-// cta_group::2 variant of the SUB = 2 kernel: two CTAs of a cluster (one TPC) work on two adjacent 32 x 8
-// pixel tiles in lockstep.  One tcgen05.mma.cta_group::2 (M = 256) covers sub-tile j of BOTH tiles; each
-// CTA stages its own activation patch but only HALF of every weight slice (output channels
-// [64 r, 64 r + 64) for rank r) -- the tensor cores read the other half from the peer's shared memory.
-// Per tile that is 87 + 144 = 231 KB of L2 -> SM traffic instead of 375 KB, and 6 KB instead of 8 KB of
-// shared-memory operand reads per MMA: the single-CTA kernel is bound by exactly those two.
-//   * rank 0 (leader) issues all MMAs; `a_full` / `g_full` live in the leader, every TMA load of either
-//     CTA completes its bytes there (.cta_group::2 loads, peer bit of the barrier address cleared);
-//   * slot releases (`a_empty`, `g_empty`) and `acc_full` reach both CTAs through a multicast commit;
-//   * `acc_empty` of the leader collects one arrive per epilogue warp of both CTAs.
-__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0,
-                                                 int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {       // same barrier offset in both CTAs
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-template <bool RES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<2>::NTHREADS, 1)
-conv3x3_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
-    using K = Cfg<2>;
-    constexpr int NTHREADS = K::NTHREADS, TILE_H = K::TILE_H;
-    constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t a_full[NA], a_empty[NA], g_full[NG_MAX], g_empty[NG_MAX], acc_full[2], acc_empty[2];
-    __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float sbias[128], sscale[128];
-
-    uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *g_ring = a_ring + NA * A_SLOT;
-    const uint32_t g_slot = 3u * p.b_slot;
-    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = p.cout;
-    uint32_t rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int first = blockIdx.x >> 1, stride = gridDim.x >> 1, npairs = (p.nitems + 1) >> 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < NG_MAX; ++s) { mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * K::EPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == K::MMA_WARP) {                                // the same warp of both CTAs, collectively
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_slot)),
-                     "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    pdl_launch_dependents();
-    stage_vec(sbias, p.bias, N, 0.f, tid, NTHREADS);
-    stage_vec(sscale, p.out_scale, N, 1.f, tid, NTHREADS);
-    tc_fence_before();
-    cluster_sync_all();                                       // barriers of both CTAs initialised, TMEM allocated
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-    pdl_wait_prior_grid();
-
-    if (warp == K::TMA_WARP) {
-        // ===================== TMA producer (both CTAs; bytes land on the leader's barriers) =====================
-        if (lane == 0) {
-            uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
-            for (int u = first; u < npairs; u += stride) {
-                const int tile = 2 * u + (int)rank;
-                const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&a_empty[sa], pa ^ 1u);                  // own slot free (multicast commit)
-                    if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * PATCH_BYTES);
-                    tma_load_3d_pair(a_ring + sa * A_SLOT, &tmA, smem_u32(&a_full[sa]) & 0xFEFFFFFFu, kc * 64,
-                                     x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
-                    if (++sa == NA) { sa = 0; pa ^= 1u; }
-                    for (int ky = 0; ky < 3; ++ky) {
-                        mbar_wait(&g_empty[sg], pg ^ 1u);
-                        if (rank == 0) mbar_expect_tx(&g_full[sg], 2u * 3u * p.b_bytes);
-                        uint8_t *dst = g_ring + sg * g_slot;
-                        const uint32_t bar = smem_u32(&g_full[sg]) & 0xFEFFFFFFu;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx)
-                            tma_load_3d_pair(dst + kx * p.b_slot, &tmB, bar, kc * 64, (int)rank * (N / 2), ky * 3 + kx);
-                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == K::MMA_WARP) {
-        // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && rank == 0) {
-            // M = 256 (two CTAs x 128 rows), N = cout; operands as in the single-CTA kernel, B holds N/2 rows
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((256u >> 4) << 24);
-            const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
-            uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
-            for (int u = first; u < npairs; u += stride, ++it) {
-                const uint32_t buf = it & 1u;
-                mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // both CTAs' epilogues drained this buffer
-                tc_fence_after();
-                const uint32_t acc = tmem_base + buf * 256u;
-                uint32_t accum = 0;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&a_full[sa], pa);
-                    const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
-                    for (int ky = 0; ky < 3; ++ky) {
-                        mbar_wait(&g_full[sg], pg);
-                        tc_fence_after();
-                        const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint32_t start = a_addr + (uint32_t)((ky + 16 * j) * PATCH_W + kx) * 128u;
-                                const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma_bf16_pair(acc + (uint32_t)(j * 128), adesc + (uint64_t)(kk * 2),
-                                                   bdesc + (uint64_t)(kk * 2), idesc, accum | (uint32_t)(kx | kk));
-                            }
-                        }
-                        accum = 1;
-                        umma_commit_pair(&g_empty[sg]);
-                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
-                    }
-                    umma_commit_pair(&a_empty[sa]);
-                    if (++sa == NA) { sa = 0; pa ^= 1u; }
-                }
-                umma_commit_pair(&acc_full[buf]);
-            }
-        }
-    } else {
-        // ===================== epilogue (warps 0 .. 15 of both CTAs) =====================
-        uint32_t rem0, rem1;                                  // the leader's acc_empty barriers, cluster addresses
-        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem0) : "r"(smem_u32(&acc_empty[0])));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(rem1) : "r"(smem_u32(&acc_empty[1])));
-        switch (p.act) {
-            case AIVC_ACT_LEAKY: epilogue_team<2, AIVC_ACT_LEAKY, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
-            case AIVC_ACT_RELU: epilogue_team<2, AIVC_ACT_RELU, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
-            case AIVC_ACT_SIGMOID: epilogue_team<2, AIVC_ACT_SIGMOID, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
-            default: epilogue_team<2, AIVC_ACT_NONE, RES, true>(p, &tmO, stage, sbias, sscale, acc_full, acc_empty, tmem_base, warp, lane, first, stride, npairs, (int)rank, rem0, rem1); break;
-        }
-    }
-
-    tc_fence_before();
-    cluster_sync_all();                                       // nobody leaves while the peer may still touch its smem / TMEM
-    if (warp == K::MMA_WARP) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    }
-}
-
-template <bool RES>
-int launch_tc3_pair(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const Tc3Params &p, int grid,
-                    size_t smem, cudaStream_t st) {
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_pair_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024));
-    AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_pair_kernel<RES>, dim3(grid), dim3(Cfg<2>::NTHREADS), smem, st, a, b, o, p));
-    AIVC_CHECK_LAUNCH("conv3x3_tc_pair_kernel");
     return 0;
 }
 
@@ -701,7 +503,6 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         mbar_wait(&bars.g_full[sg], pg);
                         tc_fence_after();
                         const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
-                        if (!(p.dbg & 4))
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
                             const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
@@ -752,16 +553,12 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
             const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
             // ---- pass 1: (acc + bias)^2 -> packed bf16 in TMEM (A operand of the norm GEMM)
-            const bool tsw = p.ts && blockIdx.x == 0 && tid == 0 && it < 30;
-            if (tsw) p.ts[it * 8 + 0] = clock64();
             mbar_wait(&bars.acc_full[buf], (it >> 1) & 1u);
-            if (tsw) p.ts[it * 8 + 1] = clock64();
             mbar_wait(&bars.xsq_empty, (it & 1u) ^ 1u);        // norm MMAs of the previous tile have read x^2
             tc_fence_after();
-            if (tsw) p.ts[it * 8 + 2] = clock64();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                if (c * 16 < per && !(p.dbg & 2)) {
+                if (c * 16 < per) {
                     const int j0 = c_lo + c * 16;
                     float v[16];
                     tmem_ld16(tl + buf * 128u + (uint32_t)j0, v);
@@ -781,13 +578,12 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.xsq_full);
-            if (tsw) p.ts[it * 8 + 3] = clock64();
             // ---- pass 2
             uint4 rr[4];
             if (RES) {                  // residual of this thread's channels: in flight while the norm GEMM runs
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (use_res && !(p.dbg & 128)) {
+                if (use_res) {
                     const __nv_bfloat16 *res_px = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, c_lo);
                     ldg_bf16x16(res_px, rr[0], rr[1]);
                     if (per == 32) ldg_bf16x16(res_px + 16, rr[2], rr[3]);
@@ -795,15 +591,13 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             mbar_wait(&bars.norm_full, it & 1u);
             tc_fence_after();
-            if (tsw) p.ts[it * 8 + 4] = clock64();
             if (staged && store_pending) {                     // staging tile still being read by the last tile's store?
                 if (leader) tma_store_wait_read();
                 named_bar_sync(1 + team, 128);
             }
-            if (tsw) p.ts[it * 8 + 5] = clock64();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                if (c * 16 < per && !(p.dbg & 8)) {
+                if (c * 16 < per) {
                     const int j0 = c_lo + c * 16;
                     float v[16], nr[16];
                     tmem_ld16(tl + buf * 128u + (uint32_t)j0, v);
@@ -850,7 +644,6 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_before();
             mbar_arrive(&bars.norm_empty);
             mbar_arrive(&bars.acc_empty[buf]);
-            if (tsw) p.ts[it * 8 + 6] = clock64();
             if (staged) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 named_bar_sync(1 + team, 128);
@@ -860,7 +653,6 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 store_pending = true;
             }
-            if (tsw) p.ts[it * 8 + 7] = clock64();
         }
         if (store_pending && leader) tma_store_wait_read();    // smem must outlive the last store's read
     }
@@ -876,8 +668,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 template <bool RES>
 int launch_tc3_gdn(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const CUtensorMap &g,
                    const Tc3Params &p, const float *beta, int inverse, int grid, size_t smem, cudaStream_t st) {
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_tc_gdn_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         225 * 1024));
+    if (smem_attr_once((const void *)conv3x3_tc_gdn_kernel<RES>, 225 * 1024)) return 1;
     AIVC_CHECK_CUDA(launch_pdl(conv3x3_tc_gdn_kernel<RES>, dim3(grid), dim3(GDN_THREADS), smem, st, a, b, o, g, p,
                                beta, inverse));
     AIVC_CHECK_LAUNCH("conv3x3_tc_gdn_kernel");
@@ -1129,31 +920,35 @@ tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 }  // namespace
 
+static int sm_count_cached() {
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sm_count = 148;
+    }
+    return sm_count;
+}
+
 // Returns -1 when the stage does not fit this kernel (caller falls through to the generic one).
 int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int cin = op->in.c, cout = op->out.c;
+    const bool x3 = op->engine == AIVC_ENGINE_TC_X3;         // split-bf16 operands, see Tc3Params
     if (op->kind != 0 || op->k != 3 || op->stride != 1) return -1;
     if (cin % 64 || cout % 16 || cout > 128) return -1;
     const bool gdn = op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN;
-    if (gdn && (cout != 128 && cout != 64)) return -1;
-    if (gdn && getenv("AIVC_TC3_NO_GDN")) return -1;         // A/B switch
-    if (op->in.dtype != AIVC_BF16 || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 8) return -1;
+    if (gdn && (x3 || (cout != 128 && cout != 64))) return -1;      // (x3 + GDN: generic kernel)
+    if (op->in.dtype != (x3 ? AIVC_BF16X2 : AIVC_BF16) || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 16) return -1;
     if (op->act_channels) return -1;
-    static const int force_sub = getenv("AIVC_TC3_SUB") ? atoi(getenv("AIVC_TC3_SUB")) : 0;   // experiment switch
     const int tiles_x = ceil_div(op->out.w, TILE_W);
     // big layers: 32-row tiles, one CTA per SM.  Fewer than two of those per SM: 16-row tiles, two CTAs
     // per SM and (wide layers) the output channels of a tile split over two work items.
     const int tiles32 = tiles_x * ceil_div(op->out.h, 32);
     int sub = tiles32 >= 296 ? 2 : 1;
     if (gdn) sub = 1;                                          // conv + GDN kernel: 16-row tiles, one CTA per SM
-    else if (force_sub == 1 || force_sub == 2) sub = force_sub;
-    else if (tiles32 >= 148 && tiles32 < 296) {
-        // one-and-a-bit waves of 32-row tiles.  AIVC_TC3_MID: 0 = generic 128-pixel-tile kernel, 1 = 16-row
-        // tiles, 2 = 32-row tiles (experiment switch)
-        static const int mid = getenv("AIVC_TC3_MID") ? atoi(getenv("AIVC_TC3_MID")) : 0;
-        if (mid == 0) return -1;
-        sub = mid;
-    }
+    else if (tiles32 >= 148 && tiles32 < 296) return -1;       // one-and-a-bit waves of 32-row tiles: the generic
+                                                               // 128-pixel-tile kernel fills the chip better (measured)
     const int tile_h = 16 * sub;
     const int ntiles = tiles_x * ceil_div(op->out.h, tile_h);
 
@@ -1164,47 +959,21 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->gate.data) p.gate = to_dev(op->gate);
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / 64;
-    // cta_group::2 pairs (every CTA stages only half of each weight slice): OPT-IN.  Measured on B200 the
-    // pair kernel is 4-10 % slower than the single-CTA kernel (125 vs 121 us at 540x960, 42 vs 37 us at
-    // 270x480): the single-CTA kernel already runs at ~93 % of cuBLAS' sustained bf16 rate there, so the
-    // halved operand traffic buys nothing and the lockstep of the two CTAs costs a little.
-    const bool pair = sub == 2 && getenv("AIVC_TC3_PAIR") != nullptr && (cout == 128 || cout == 64);
-    // small layers (SUB = 1): AIVC_TC3_SMALL = 0 (default): channel split, two CTAs per SM, shallow ring;
-    // 1: no split, one CTA per SM, deep weight ring; 2: split, one CTA per SM, deep ring  (experiment)
-    static const int small_mode = getenv("AIVC_TC3_SMALL") ? atoi(getenv("AIVC_TC3_SMALL")) : 0;
-    p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296 && small_mode != 1) ? 2 : 1;
+    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? 3 : 1) * p.kchunks; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
+    // small layers (SUB = 1): output channels split over two work items, two CTAs per SM, shallow weight ring
+    p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
     p.ncta = cout / p.nsplit;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.in_pad = op->in.pad;
-    p.b_bytes = (uint32_t)(pair ? cout / 2 : p.ncta) * 128u;    // weight rows one CTA stages per tap
+    p.b_bytes = (uint32_t)p.ncta * 128u;                       // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
-    { const char *e = getenv("AIVC_TC3_DBG"); p.dbg = e ? atoi(e) : 0; }
-    static long long *ts_dev = nullptr;
-    if (getenv("AIVC_TC3_TS")) {                             // debug: clock64 timeline of CTA 0 (device memory)
-        long long ts_buf[240];
-        if (!ts_dev) cudaMalloc(&ts_dev, sizeof(ts_buf));
-        else {                                               // dump the previous launch's timeline
-            cudaDeviceSynchronize();
-            cudaMemcpy(ts_buf, ts_dev, sizeof(ts_buf), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "ts kernel: init+alloc %lld, stage+sync %lld, pdl wait %lld, body %lld, sync %lld, dealloc %lld\n",
-                    ts_buf[1] - ts_buf[0], ts_buf[2] - ts_buf[1], ts_buf[3] - ts_buf[2], ts_buf[4] - ts_buf[3],
-                    ts_buf[5] - ts_buf[4], ts_buf[6] - ts_buf[5]);
-            for (int t = 0; t < 12 && getenv("AIVC_TC3_TS_TILES"); ++t) {
-                fprintf(stderr, "ts tile %2d:", t);
-                for (int k = 1; k < 8; ++k) fprintf(stderr, " %6lld", ts_buf[t * 8 + k] - ts_buf[t * 8 + k - 1]);
-                fprintf(stderr, "  | period %6lld\n", t ? ts_buf[t * 8] - ts_buf[(t - 1) * 8] : 0LL);
-            }
-        }
-        cudaMemset(ts_dev, 0, sizeof(ts_buf));
-        p.ts = ts_dev;
-    }
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
     const size_t gdn_bytes = gdn ? (size_t)cout * cout * 2 + 2 * STAGE_BYTES : 0;   // gamma + two more staging tiles
     const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES + gdn_bytes;
     // SUB = 1 aims at two CTAs per SM (<= 111 KB each) when two weight groups fit in that
     const size_t two_cta = 111 * 1024;
-    const bool two_per_sm = sub == 1 && !gdn && small_mode == 0 && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
-    const size_t budget = sub == 2 ? 219 * 1024 : (two_per_sm ? two_cta : (gdn ? 224 * 1024 : (small_mode ? 219 * 1024 : 165 * 1024)));
+    const bool two_per_sm = sub == 1 && !gdn && fixed + 2 * 3 * (size_t)p.b_slot <= two_cta;
+    const size_t budget = sub == 2 ? 219 * 1024 : (two_per_sm ? two_cta : (gdn ? 224 * 1024 : 165 * 1024));
     p.ng = NG_MAX;
     while (fixed + (size_t)p.ng * 3 * p.b_slot > budget && p.ng > 1) --p.ng;
     if (p.ng < 2) return -1;
@@ -1212,29 +981,30 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const aivc_fmap &in = op->in;
     const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
     CUtensorMap tmA, tmB;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
+    {   // (a split-bf16 view also reaches its lo half at + c_stride / 2)
+        cuuint64_t dims[3] = {(cuuint64_t)(x3 ? p.a_lo + cin : cin), (cuuint64_t)(in.w + 2 * in.pad), (cuuint64_t)(in.h + 2 * in.pad)};
         cuuint64_t strides[2] = {pix_b, row_b};
         cuuint32_t box[3] = {64, PATCH_W, (cuuint32_t)(tile_h + 2)};
         if (encode_map(&tmA, (char *)in.data + (size_t)in.c_off * 2, 3, dims, strides, box, 128, "A/3x3")) return 1;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
-        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)(pair ? cout / 2 : p.ncta), 1};
+        const int wcin = x3 ? 2 * cin : cin;                   // x3: [tap][cout][hi cin | lo cin]
+        cuuint64_t dims[3] = {(cuuint64_t)wcin, (cuuint64_t)cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)wcin * 2, (cuuint64_t)wcin * cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.ncta, 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, 128, "B/3x3")) return 1;
     }
     CUtensorMap tmO;
     memset(&tmO, 0, sizeof(tmO));
     const aivc_fmap &o = op->out;
     // staged epilogue (smem + TMA store, residual prefetched into registers): bf16 output in 32-channel
-    // multiples, no gate, residual (if any) bf16 with 16-byte aligned channel groups
+    // multiples, no gate, residual (if any) bf16 with 16-byte aligned channel groups.  Split-bf16 and fp32
+    // outputs take the generic per-thread stores.
     const aivc_fmap &rs = op->residual;
     const bool res_ok = !rs.data || (rs.dtype == AIVC_BF16 && rs.c_off % 8 == 0 && rs.c_stride % 8 == 0 &&
                                      ((uintptr_t)rs.data & 15) == 0);
-    p.tma_store = (o.dtype == AIVC_BF16 && o.c_off % 8 == 0 && o.c_stride % 8 == 0 && p.ncta % 32 == 0 &&
-                   ((uintptr_t)o.data & 15) == 0 && !op->gate.data && res_ok &&
-                   getenv("AIVC_TC3_NO_TMA_STORE") == nullptr) ? 1 : 0;
+    p.tma_store = (!x3 && o.dtype == AIVC_BF16 && o.c_off % 8 == 0 && o.c_stride % 8 == 0 && p.ncta % 32 == 0 &&
+                   ((uintptr_t)o.data & 15) == 0 && !op->gate.data && res_ok) ? 1 : 0;
     if (p.tma_store) {
         const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
         cuuint64_t dims[3] = {(cuuint64_t)cout, (cuuint64_t)o.w, (cuuint64_t)o.h};     // interior only: OOB rows/cols are clipped
@@ -1244,12 +1014,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         if (encode_map(&tmO, base, 3, dims, strides, box, 64, "O/3x3")) return 1;
     }
     const size_t smem = fixed + (size_t)p.ng * 3 * p.b_slot;
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        AIVC_CHECK_CUDA(cudaGetDevice(&dev));
-        AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sm_count = sm_count_cached();
     const bool res = p.tma_store && rs.data;                 // residual prefetched into registers
     g_aivc_kernel_class = gdn ? AIVC_KC_TC3_GDN : AIVC_KC_TC3;
     if (gdn) {
@@ -1263,11 +1028,6 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         return res ? launch_tc3_gdn<true>(tmA, tmB, tmO, tmG, p, op->gdn_beta, inverse, grid, smem, st)
                    : launch_tc3_gdn<false>(tmA, tmB, tmO, tmG, p, op->gdn_beta, inverse, grid, smem, st);
     }
-    if (pair) {
-        const int npairs = (ntiles + 1) / 2, nclusters = sm_count / 2;
-        const int grid = 2 * (npairs < nclusters ? npairs : nclusters);
-        return res ? launch_tc3_pair<true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3_pair<false>(tmA, tmB, tmO, p, grid, smem, st);
-    }
     const int slots = sm_count * (two_per_sm ? 2 : 1);
     const int grid = p.nitems < slots ? p.nitems : slots;
     if (sub == 1) return res ? launch_tc3<1, true>(tmA, tmB, tmO, p, grid, smem, st) : launch_tc3<1, false>(tmA, tmB, tmO, p, grid, smem, st);
@@ -1276,8 +1036,6 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
 
 // Transposed 3x3 stride-2 stage on the persistent kernel above; -1 = not eligible.
 int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
-    static const bool off = getenv("AIVC_NO_TCONV3") != nullptr;        // A/B switch
-    if (off) return -1;
     const int cin = op->in.c, cout = op->out.c;
     if (op->kind != 1 || op->k != 3 || op->stride != 2) return -1;
     if (cin % 64 || cin > 128 || cout % 32 || cout > 128) return -1;
@@ -1324,14 +1082,9 @@ int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
         void *base = (char *)o.data + ((size_t)o.pad * o.pitch + o.pad) * opix + (size_t)o.c_off * 2;
         if (encode_map(&tmO, base, 5, dims, strides, box, 64, "O/tconv3")) return 1;
     }
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        AIVC_CHECK_CUDA(cudaGetDevice(&dev));
-        AIVC_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sm_count = sm_count_cached();
     g_aivc_kernel_class = AIVC_KC_TCONV3;
-    AIVC_CHECK_CUDA(cudaFuncSetAttribute(tconv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    if (smem_attr_once((const void *)tconv3x3_tc_kernel, 225 * 1024)) return 1;
     const int grid = ntiles < sm_count ? ntiles : sm_count;
     AIVC_CHECK_CUDA(launch_pdl(tconv3x3_tc_kernel, dim3(grid), dim3(Cfg<2>::NTHREADS), smem, st, tmA, tmB, tmO, p));
     AIVC_CHECK_LAUNCH("tconv3x3_tc_kernel");

@@ -2,7 +2,6 @@
 // motion-compensation warp + blend, hyperprior mu/sigma, quantisation + integer CDF bounds.
 // One thread per pixel (or per symbol); channel counts here are 1..6 at full resolution and
 // C_y at latent resolution, so the work is a single pass over the data.
-#include <stdlib.h>
 #include "common.cuh"
 extern int g_aivc_kernel_class;
 #include "laplace_cdf.h"
@@ -442,64 +441,6 @@ __global__ void col2im_tconv_kernel(FMap P, FMap out, const float *__restrict__ 
 }
 
 
-// Tiled col2im for fp16 partial sums: a block stages the P records of a (TY+2) x (TX+2) input-pixel tile in
-// shared memory with fully coalesced 8-byte loads (a record is the k*k*co partial sums of one input pixel,
-// contiguous), then every thread gathers its output pixels (<= 9 records each) from shared memory.  Global
-// traffic: P read 1.2 times (halo), output written once.  Record stride is padded by 8 bytes so that the
-// 16 threads of a warp reading the same tap of neighbouring records hit 16 different banks.
-constexpr int C2I_TX = 32, C2I_TY = 16, C2I_THREADS = 256;
-__global__ void __launch_bounds__(C2I_THREADS) col2im_tconv_tiled_kernel(FMap P, FMap out, const float *__restrict__ bias,
-                                                                         int k, int act, int rec_words) {
-    extern __shared__ uint2 c2i_smem[];                        // [(TY+2)][(TX+2)][rec_words 8-byte words]
-    const int co_n = out.c, pad = (k + 1) / 2 - 1;
-    const int tiles_x = (P.w + C2I_TX - 1) / C2I_TX;
-    const int x0 = (blockIdx.x % tiles_x) * C2I_TX, y0 = (blockIdx.x / tiles_x) * C2I_TY;
-    const int src_words = P.c_stride / 4;                      // 8-byte words per global record
-    const uint2 *g = reinterpret_cast<const uint2 *>((const __half *)P.data + P.c_off);
-    // ---- stage (zeros outside the image: those records do not exist)
-    const int n_words = (C2I_TY + 2) * (C2I_TX + 2) * src_words;
-    for (int i = threadIdx.x; i < n_words; i += C2I_THREADS) {
-        const int w = i % src_words, px = (i / src_words) % (C2I_TX + 2), py = i / (src_words * (C2I_TX + 2));
-        const int iy = y0 - 1 + py, ix = x0 - 1 + px;
-        uint2 v = make_uint2(0u, 0u);
-        if (iy >= 0 && iy < P.h && ix >= 0 && ix < P.w) v = g[((size_t)iy * P.pitch + ix) * src_words + w];
-        c2i_smem[(py * (C2I_TX + 2) + px) * rec_words + w] = v;
-    }
-    __syncthreads();
-    // ---- gather: thread -> output column (of 2*TX), rows strided by 4
-    const __half *sm = reinterpret_cast<const __half *>(c2i_smem);
-    const int rec_halves = rec_words * 4;
-    const int oxl = threadIdx.x % (2 * C2I_TX), ox = 2 * x0 + oxl;
-    for (int oyl = threadIdx.x / (2 * C2I_TX); oyl < 2 * C2I_TY; oyl += C2I_THREADS / (2 * C2I_TX)) {
-        const int oy = 2 * y0 + oyl;
-        if (oy >= out.h || ox >= out.w) continue;
-        float acc[8];
-        for (int c = 0; c < co_n; ++c) acc[c] = bias ? bias[c] : 0.f;
-        for (int ky = (oy + pad) & 1; ky < k; ky += 2) {
-            const int iy = (oy + pad - ky) >> 1;               // (oy + pad - ky is even; may be -2 -> iy = -1: zero record)
-            const int pyl = iy - (y0 - 1);
-            if (pyl < 0 || pyl >= C2I_TY + 2) continue;
-            for (int kx = (ox + pad) & 1; kx < k; kx += 2) {
-                const int ix = (ox + pad - kx) >> 1;
-                const int pxl = ix - (x0 - 1);
-                if (pxl < 0 || pxl >= C2I_TX + 2) continue;
-                const __half *r = sm + (size_t)(pyl * (C2I_TX + 2) + pxl) * rec_halves + (ky * k + kx) * co_n;
-                if (co_n == 6) {                               // 12-byte group, 4-byte aligned: three half2 loads
-                    const __half2 *r2 = reinterpret_cast<const __half2 *>(r);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float2 f = __half22float2(r2[c]);
-                        acc[2 * c] += f.x; acc[2 * c + 1] += f.y;
-                    }
-                } else {
-                    for (int c = 0; c < co_n; ++c) acc[c] += __half2float(r[c]);
-                }
-            }
-        }
-        for (int c = 0; c < co_n; ++c) fm_store(out, oy, ox, c, act_apply(act, acc[c]));
-    }
-}
-
 // ---------------------------------------------------------------- weight re-layout
 __global__ void pack_weight_kernel(const float *__restrict__ src, void *__restrict__ dst, int kind,
                                    int k, int cin, int cout, int engine, int cin_pad, int cout_pad,
@@ -525,7 +466,11 @@ __global__ void pack_weight_kernel(const float *__restrict__ src, void *__restri
             v = src[s] * scale;
         }
         if (engine == AIVC_ENGINE_SIMT) ((float *)dst)[i] = v;
-        else ((__nv_bfloat16 *)dst)[i] = __float2bfloat16_rn(v);
+        else if (engine == AIVC_ENGINE_TC_X3) {    // [tap][cout_pad][hi cin_pad | lo cin_pad]
+            const size_t row = i / cin_pad, col = i % cin_pad;
+            __nv_bfloat16 *d = (__nv_bfloat16 *)dst + row * 2 * cin_pad + col;
+            bf16_split(v, d[0], d[cin_pad]);
+        } else ((__nv_bfloat16 *)dst)[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -560,22 +505,6 @@ int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->out.c > 8) AIVC_FAIL("col2im: at most 8 output channels, got %d", op->out.c);
     if (op->in.c < op->k * op->k * op->out.c) AIVC_FAIL("col2im: input has %d channels, needs %d", op->in.c, op->k * op->k * op->out.c);
     if (op->out.h != 2 * op->in.h || op->out.w != 2 * op->in.w) AIVC_FAIL("col2im: output must be exactly 2x");
-    const aivc_fmap &P = op->in;
-    if (P.dtype == AIVC_F16 && P.pad == 0 && P.c_stride % 4 == 0 && P.c_off % 4 == 0 && ((uintptr_t)P.data & 7) == 0 &&
-        getenv("AIVC_C2I_TILED") != nullptr) {      // opt-in: measured SLOWER (392 vs 253 us for the 6-channel output
-                                                   // layer: one 200 KB block per SM, staging not overlapped with the gather)
-        const int rec_words = P.c_stride / 4 + 1;              // + 8 bytes: bank spreading
-        const size_t smem = (size_t)(C2I_TY + 2) * (C2I_TX + 2) * rec_words * 8;
-        if (smem <= 226 * 1024) {
-            AIVC_CHECK_CUDA(cudaFuncSetAttribute(col2im_tconv_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-            const int blocks = ceil_div(P.w, C2I_TX) * ceil_div(P.h, C2I_TY);
-            col2im_tconv_tiled_kernel<<<blocks, C2I_THREADS, smem, st>>>(to_dev(P), to_dev(op->out), op->bias, op->k,
-                                                                         op->act, rec_words);
-            AIVC_CHECK_LAUNCH("col2im_tconv_tiled");
-            return 0;
-        }
-    }
     col2im_tconv_kernel<<<grid_for((size_t)op->out.h * op->out.w), PT, 0, st>>>(to_dev(op->in), to_dev(op->out), op->bias,
                                                                                 op->k, op->act);
     AIVC_CHECK_LAUNCH("col2im_tconv");
@@ -789,7 +718,7 @@ int aivc_dequantize_latent(const int16_t *q, const aivc_fmap *hs, const float *d
 }
 
 size_t aivc_packed_weight_bytes(int k, int engine, int cin_pad, int cout_pad) {
-    return (size_t)k * k * cin_pad * cout_pad * (engine == AIVC_ENGINE_SIMT ? sizeof(float) : 2);
+    return (size_t)k * k * cin_pad * cout_pad * (engine == AIVC_ENGINE_TC ? 2 : 4);     // (TC_X3: two bf16 per weight)
 }
 
 int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin, int cout, int engine,

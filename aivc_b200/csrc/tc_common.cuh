@@ -509,6 +509,9 @@ inline int encode_map(CUtensorMap *m, void *base, int rank, const cuuint64_t *di
 }
 
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize sticks to (function, device): set it once, not per launch
+int smem_attr_once(const void *kernel, int bytes);       // api.cu (mutex-protected table); 0 = ok
+
 // launch with the programmatic-stream-serialization attribute (PDL)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

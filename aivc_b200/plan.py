@@ -25,15 +25,19 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import FMap, ConvOp, ACT, POST, F32, BF16, F16, ENGINE_SIMT, ENGINE_TC
+from ._lib import FMap, ConvOp, ACT, POST, F32, BF16, F16, BF16X2, ENGINE_SIMT, ENGINE_TC, ENGINE_TC_X3
 
-_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16, BF16X2: torch.bfloat16}
 
 
 @dataclass
 class Config:
-    precision: str = 'bf16'        # 'fp32': every stage on the exact SIMT engine, fp32 buffers
-                                   # 'bf16': tcgen05 engine wherever the channel counts allow
+    precision: str = 'bf16x3'      # 'fp32'  : every stage on the exact SIMT engine, fp32 buffers
+                                   # 'bf16x3': tcgen05 engine on split-bf16 operands (hi.Whi + lo.Whi + hi.Wlo per
+                                   #           K chunk, fp32 accumulation): fp32-grade results, 3x the MMA work --
+                                   #           the mode whose latent indices match the fp32 reference
+                                   # 'bf16'  : tcgen05 engine on plain bf16 operands: fastest, ~1 % of the latent
+                                   #           indices differ from fp32 arithmetic
     tc_min_cin: int = 16           # tensor-core stages need cin % 16 == 0 and cout % 16 == 0
     hyper: str = 'auto'            # precision of h_a / h_s: 'fp32' (exact engine), 'bf16', or
                                    # 'auto' = same as `precision`
@@ -42,6 +46,15 @@ class Config:
 
     def key(self):
         return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first)
+
+    @property
+    def tc(self):
+        return self.precision in ('bf16', 'bf16x3')
+
+    @property
+    def act_dtype(self):
+        """dtype of tensors a tensor-core stage reads"""
+        return BF16X2 if self.precision == 'bf16x3' else BF16
 
     def hyper_cfg(self):
         h = self.precision if self.hyper == 'auto' else self.hyper
@@ -59,17 +72,26 @@ class Buffer:
         self.h, self.w, self.c, self.pad, self.dtype = h, w, c, pad, dtype
         self.pitch = w + 2 * pad + ((w + 2 * pad) & 1)      # even: stride-2 TMA views pair columns
         self.rows = h + 2 * pad + ((h + 2 * pad) & 1)
-        self.t = torch.zeros(self.rows * self.pitch * c, dtype=_TORCH_DT[dtype], device=device)
+        # split bf16: a pixel is [hi(c) | lo(c)], 2c elements
+        self.c_stride = 2 * c if dtype == BF16X2 else c
+        self.t = torch.zeros(self.rows * self.pitch * self.c_stride, dtype=_TORCH_DT[dtype], device=device)
 
     def view(self, c_off=0, c=None, h=None, w=None):
         return FMap(self.t.data_ptr(), self.h if h is None else h, self.w if w is None else w,
-                    self.c - c_off if c is None else c, c_off, self.c, self.pad, self.pitch,
+                    self.c - c_off if c is None else c, c_off, self.c_stride, self.pad, self.pitch,
                     self.rows, self.dtype, 0)
 
     def interior(self):
-        """[h, w, c] torch view of the logical tensor (debug / tests)."""
-        full = self.t.view(self.rows, self.pitch, self.c)
-        return full[self.pad:self.pad + self.h, self.pad:self.pad + self.w]
+        """[h, w, c] torch view of the logical tensor (debug / tests; split bf16: the hi halves)."""
+        full = self.t.view(self.rows, self.pitch, self.c_stride)
+        return full[self.pad:self.pad + self.h, self.pad:self.pad + self.w, :self.c]
+
+    def zero_channels(self, c0, c1):
+        """channels [c0, c1) of every pixel, border included, := 0 (stream-ordered)"""
+        full = self.t.view(self.rows, self.pitch, self.c_stride)
+        full[:, :, c0:c1].zero_()
+        if self.dtype == BF16X2:
+            full[:, :, self.c + c0:self.c + c1].zero_()
 
 
 @dataclass
@@ -280,9 +302,9 @@ class Plan:
                 if s.src is self.src:
                     s.cin_off, s.w_scale = off, wsc
             self.src.c = buf_c
-        if cfg.precision == 'bf16':
+        if cfg.tc:
             self._split_narrow_tconvs()
-            if in_embed is not None and cfg.s2d_first:
+            if in_embed is not None and cfg.s2d_first and cfg.precision == 'bf16':
                 self._space_to_depth_first_layer()
         last = self.stages[-1]
         self.out_c = self.dst.c
@@ -348,7 +370,7 @@ class Plan:
 
     # -- engine / dtype / border selection
     def _choose_engines(self):
-        tc = self.cfg.precision == 'bf16'
+        tc, x3 = self.cfg.tc, self.cfg.precision == 'bf16x3'
         for s in self.stages:
             if s.kind == 3:
                 s.engine = ENGINE_SIMT
@@ -356,18 +378,18 @@ class Plan:
                 continue
             if s.kind == 2:
                 s.engine = ENGINE_SIMT
-                if tc:          # partial sums of the pixel-domain output: fp16 (11-bit mantissa), half the bytes of fp32
+                if tc and not x3:   # partial sums of the pixel-domain output: fp16 (11-bit mantissa), half the bytes of fp32
                     s.src.dtype = F16
                 continue
             cin, cout = s.src.c, s.dst.c
             ok = tc and cin % self.cfg.tc_min_cin == 0 and cout % 16 == 0 and cout <= 256
             if s.gdn is not None and cout > 128:
                 ok = False
-            s.engine = ENGINE_TC if ok else ENGINE_SIMT
+            s.engine = (ENGINE_TC_X3 if x3 else ENGINE_TC) if ok else ENGINE_SIMT
         for s in self.stages:
-            if s.engine == ENGINE_TC:
+            if s.engine != ENGINE_SIMT:
                 assert s.src.dtype != F16
-                s.src.dtype = BF16
+                s.src.dtype = self.cfg.act_dtype
                 if s.kind == 0 and s.k > 1:
                     s.src.pad = max(s.src.pad, s.k // 2)
                 # skip / trunk tensors that only ever feed an epilogue (ChengResBlock aux path, attention
@@ -375,7 +397,7 @@ class Plan:
                 # consumer prefetches them as packed 16-byte groups
                 for t in (s.res, s.gate):
                     if t is not None and not t.external:
-                        t.dtype = BF16
+                        t.dtype = self.cfg.act_dtype
 
     def _assign_buffers(self, src_buf, src_c_off, dst_into, in_dtype):
         for i, s in enumerate(self.stages):
@@ -463,6 +485,10 @@ class Plan:
                     scratch = torch.empty(cout * s.dst.h * s.dst.w, dtype=torch.float32, device=dev)
                     op.scratch = scratch.data_ptr()
                     self._keep.append(scratch)
+                elif s.engine == ENGINE_TC_X3:
+                    g_hi = gamma.to(dev).to(torch.bfloat16)             # [i][hi j | lo j]
+                    g_lo = (gamma.to(dev) - g_hi.float()).to(torch.bfloat16)
+                    gm = torch.cat([g_hi, g_lo], dim=1).contiguous()
                 else:
                     gm = gamma.to(dev).to(torch.bfloat16).contiguous()  # [i][j], K-major B operand
                 op.gdn_beta, op.gdn_gamma = beta.data_ptr(), gm.data_ptr()

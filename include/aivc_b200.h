@@ -54,7 +54,10 @@ enum {
     AIVC_POST_ROUND_CLAMP = 3  /* Quantizer at eval + AC range clamp  misc_layers.py:167 */
 };
 
-enum { AIVC_ENGINE_SIMT = 0, AIVC_ENGINE_TC = 1 };
+enum { AIVC_ENGINE_SIMT = 0, AIVC_ENGINE_TC = 1,
+       AIVC_ENGINE_TC_X3 = 2 /* tensor cores on split-bf16 operands (AIVC_BF16X2 input, weights packed
+                              * [tap][cout][hi cin | lo cin]): hi.Whi + lo.Whi + hi.Wlo per K chunk, fp32
+                              * accumulation in TMEM -- fp32-grade results (the "bf16x3" precision mode) */ };
 
 /* A view on an NHWC feature map living in a (possibly wider, possibly bordered) buffer.
  * element (y, x, ch) of the view is at
