@@ -164,10 +164,22 @@ def randomize_(model, seed):
     return model
 
 
-def build_standin(seed=1234, C=128, Cy=64, Cz=64, Csc=64):
+def build_standin(seed=1234, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=None):
     """Seeded stand-in FullNet (default PyTorch conv init, GDN default init, Balle
-    xavier init -- SURVEY.md 8(d)) in eval mode on the CPU."""
+    xavier init -- SURVEY.md 8(d)) in eval mode on the CPU.
+    hyper_boost=(a, s): scale the last layer of h_a by `a` and the weights of the last layer of h_s by `s`.
+    Untrained hyper transforms shrink their input ~10x per layer, so without it every z rounds to zero and
+    mu / sigma are spatially constant; (12, 8) gives z indices with a spread of ~1.5 and a sigma that varies
+    by ~2x over the latent, i.e. a hyperprior that actually steers the range coder."""
     torch.manual_seed(seed)
     net = FullNet(C, Cy, Cz, Csc)
     randomize_(net, seed + 1)
+    if hyper_boost is not None:
+        a, s_ = hyper_boost
+        with torch.no_grad():
+            for cn in (net.mode_net.mode_net, net.codec_net.codec_net):
+                last = cn.h_a[-1].layers[1]
+                last.weight.mul_(a)
+                last.bias.mul_(a)
+                cn.h_s[-1].layers[1].weight.mul_(s_)
     return net.eval()

@@ -300,7 +300,7 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split bf16 operands, fp32 accumulate)', 'fp32': 'f32'}[args.precision],
             'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': frame_bytes * len(names), 'd2h_bytes_per_step': frame_bytes * len(names),
@@ -343,7 +343,7 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--stage-csv', default='', help='dump per-stage CUDA-event timings of the timed region')
     args = ap.parse_args()

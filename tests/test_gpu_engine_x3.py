@@ -1,0 +1,96 @@
+"""GPU suite for the bf16x3 engine: tcgen05 on split-bf16 operands (hi.Whi + lo.Whi + hi.Wlo, fp32 accumulation).
+
+Tolerance: an activation / weight is represented as hi + lo with 16 significant bits (2^-17 relative) and the
+lo.Wlo product is dropped, so one fused stage lands within ~5e-6 (rms, relative) of the fp32 oracle and a
+multi-stage block within ~6e-6 (measured on B200: tools/x3_check.py); required here
+    rms(y - ref) <= 2e-5 rms(ref)      max|y - ref| <= 5e-5 max|ref|
+-- 500x tighter than the plain-bf16 engine's tolerance, 30x looser than the exact fp32 engine's."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.leafcfg import LEAVES, load_leaf
+from tests.test_gpu_engine_tc import WIDE
+
+pytestmark = pytest.mark.gpu
+RMS_TOL, MAX_TOL = 2e-5, 5e-5
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def _cfg():
+    from aivc_b200.plan import Config
+    return Config(precision='bf16x3')
+
+
+def _check(y, ref):
+    err = y - ref
+    rms = np.sqrt((err ** 2).mean()) / max(np.sqrt((ref ** 2).mean()), 1e-12)
+    mx = np.abs(err).max() / max(np.abs(ref).max(), 1e-12)
+    assert rms <= RMS_TOL and mx <= MAX_TOL, 'rms %.2e (tol %.0e), max %.2e (tol %.0e)' % (rms, RMS_TOL, mx, MAX_TOL)
+
+
+@pytest.mark.parametrize('name', sorted(LEAVES))
+def test_leaf_x3_vs_reference_golden(name, golden_dir, dev):
+    from aivc_b200 import plan
+    m, fx = load_leaf(name, golden_dir)
+    for i in range(2):
+        y = plan.run_module(m, torch.from_numpy(fx['x%d' % i]).to(dev), _cfg()).cpu().numpy()
+        _check(y, fx['y%d' % i])
+
+
+@pytest.mark.parametrize('name', sorted(WIDE))
+@pytest.mark.parametrize('size', [(33, 47), (135, 243), (270, 481)])
+def test_wide_layers_x3_vs_oracle(name, size, dev):
+    """Every kernel the split-bf16 mode runs on (persistent 3x3 at >= 120 tiles, generic kernel incl. chained
+    GDN, stride 2 and transposed phases), odd sizes and partial tiles, against the CPU fp32 oracle."""
+    import aivc_b200.layers as M
+    from aivc_b200 import plan
+    from aivc_b200._lib import ENGINE_TC_X3
+    from oracle import nn_ref as R
+    if size[0] == 270 and name not in ('conv3_s1_leaky_128', 'cheng_plain_128', 'cheng_down_128', 'up3_no_128'):
+        pytest.skip('large size only for the persistent-kernel shapes')
+    mk, cin, _ = WIDE[name]
+    torch.manual_seed(hash(name) % 1000)
+    m = mk(M).eval()
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if n_.endswith('gamma'):
+                p.add_(0.02 * torch.rand_like(p))
+    h, w = size
+    x = torch.randn(1, cin, h, w, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = R.forward_module(m, x).numpy()
+    y = plan.run_module(m, x.to(dev), _cfg()).cpu().numpy()
+    p = next(iter(m.__dict__[plan._CACHE_ATTR].values()))
+    assert all(s.engine == ENGINE_TC_X3 for s in p.stages), [s.engine for s in p.stages]
+    assert y.shape == ref.shape
+    _check(y, ref)
+
+
+def test_codec_x3_bytes_identical_to_oracle(golden_dir, dev):
+    """The golden 80x112 GOP (I, P, B): the split-bf16 engine produces the oracle's bitstream bytes and the
+    oracle's 8-bit reconstruction exactly, and decoder == encoder."""
+    from aivc_b200 import models, gop as G
+    from aivc_b200.codec import FrameCodec, planes_to_device
+    fx = np.load(os.path.join(golden_dir, 'system_80x112.npz'))
+    h, w = int(fx['H']), int(fx['W'])
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    gop = G.generate_gop_struct('1_GOP_2')
+    frames = {'frame_%d' % t: planes_to_device([fx['src_frame_%d_%s' % (t, k)] for k in 'yuv'], dev)
+              for t in range(3)}
+    codec = FrameCodec(net, h, w, dev, _cfg())
+    bts, rec = codec.encode_gop(frames, gop)
+    dec = codec.decode_gop(bts, gop)
+    for f in gop:
+        for a, b in zip(rec[f], dec[f]):
+            assert torch.equal(a, b)
+        for k, p in zip('yuv', rec[f]):
+            assert np.array_equal(p.cpu().numpy(), fx['spec_rec_%s_%s' % (f, k)].reshape(-1)), (f, k)
+        assert bts[f] == fx['spec_bytes_%s' % f].tobytes(), f

@@ -116,7 +116,7 @@ def _noise_gops(n_gops, h, w, seed, dev):
              for t in range(3)} for _ in range(n_gops)]
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
 def test_multi_gop_decode_with_lagging_gpu(precision, dev):
     """Round-1 driver failure, reproduced on purpose: decode_video enqueues GOP after GOP without a stream
     synchronisation, so the host runs ahead of the GPU.  Here the GPU is held back by a long sleep kernel and
@@ -159,7 +159,7 @@ def test_multi_gop_decode_with_lagging_gpu(precision, dev):
             del eng.synth_launch
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
 def test_encoder_is_run_to_run_deterministic(precision, dev):
     """The same GOP coded 20 times on one codec (and once on a fresh one) gives identical bytes and identical
     planes: fixed accumulation order, no atomics, no stale staging memory.  This is what

@@ -45,7 +45,7 @@ src = {f: [p.reshape(-1) for p in clip[i]] for i, f in enumerate(names)}
 out = {'geometry': '%dx%d, GOP 1_GOP_2 (I, P, B), stand-in C=128 Cy=Cz=64, synthetic frames' % (W, H),
        'oracle_seconds': round(t_oracle, 1), 'oracle_bytes': {f: len(o_bytes[f]) for f in names}}
 frames = {f: planes_to_device(clip[i], dev) for i, f in enumerate(names)}
-for prec in ('fp32', 'bf16'):
+for prec in ('fp32', 'bf16x3', 'bf16'):
     codec = FrameCodec(net, H, W, dev, Config(precision=prec))
     # I frame alone: latent indices of the CodecNet
     codec.encode_gop({'frame_0': frames['frame_0']}, G.generate_gop_struct('1_GOP_0'))
