@@ -385,6 +385,8 @@ int launch_tc3(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o,
 //     columns [0,256)   acc[buf] = conv(x)                       (main loop, as above; double buffered)
 //     columns [256,384) norm     = (acc+bias)^2 . gamma^T         (8 MMAs per tile)
 //     columns [384,448) (acc+bias)^2 as packed bf16: the A operand of the norm GEMM, read from TMEM
+//     columns [448,512) split-bf16 mode only: the lo half of (acc+bias)^2 (norm = hi.Ghi + lo.Ghi + hi.Glo,
+//                       gamma resident as [hi | lo], 2 N^2 bf16)
 // Epilogue pass 1 (16 warps, one pixel x N/4 channels per thread) reads acc and writes (acc+bias)^2 back to
 // TMEM (tcgen05.st); the MMA thread multiplies it with gamma (resident in shared memory for the whole
 // kernel) between two weight groups of the NEXT tile's main loop, as soon as the operand is there; pass 2
@@ -414,8 +416,8 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t *a_ring = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *g_ring = a_ring + NA * A_SLOT;
     const uint32_t g_slot = 3u * p.b_slot;
-    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB
-    uint8_t *gam = stage + 4 * STAGE_BYTES;                   // [nk][N rows][128 B], 128B swizzle (TMA)
+    uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB (none in split-bf16 mode)
+    uint8_t *gam = stage + (p.x3 ? 0 : 4 * STAGE_BYTES);      // [nk (x3: 2 nk)][N rows][128 B], 128B swizzle (TMA)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -444,15 +446,18 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     if (warp == GDN_TMA_WARP) {
         if (lane == 0) {
-            mbar_expect_tx(&bars.gamma_full, (uint32_t)(N * N * 2));             // gamma: once per CTA
-            for (int c = 0; c < nk; ++c) tma_load_2d(gam + (size_t)c * N * 128, &tmG, &bars.gamma_full, c * 64, 0);
+            const int ngam = p.x3 ? 2 * nk : nk;                                 // gamma ([hi | lo]): once per CTA
+            mbar_expect_tx(&bars.gamma_full, (uint32_t)(ngam * N * 128));
+            for (int c = 0; c < ngam; ++c) tma_load_2d(gam + (size_t)c * N * 128, &tmG, &bars.gamma_full, c * 64, 0);
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
             for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x) {
                 const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < p.kv; ++kc) {
+                    int ca, cb;
+                    chunk_coords(p, kc, ca, cb);
                     mbar_wait(&bars.a_empty[sa], pa ^ 1u);
                     mbar_expect_tx(&bars.a_full[sa], PATCH_BYTES);
-                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &bars.a_full[sa], kc * 64, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
+                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &bars.a_full[sa], ca, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
                     for (int ky = 0; ky < 3; ++ky) {
                         mbar_wait(&bars.g_empty[sg], pg ^ 1u);
@@ -460,7 +465,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx)
-                            tma_load_3d(dst + kx * p.b_slot, &tmB, &bars.g_full[sg], kc * 64, 0, ky * 3 + kx);
+                            tma_load_3d(dst + kx * p.b_slot, &tmB, &bars.g_full[sg], cb, 0, ky * 3 + kx);
                         if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                     }
                 }
@@ -476,13 +481,15 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&bars.norm_empty, (k & 1u) ^ 1u);                      // pass 2 of tile k-1 has read norm
                 mbar_wait(&bars.xsq_full, k & 1u);                               // pass 1 of tile k has written x^2
                 tc_fence_after();
-                for (int c = 0; c < nk; ++c) {
-                    const uint64_t bd = make_desc(smem_u32(gam + (size_t)c * N * 128), 128);
+                for (int part = 0; part < (p.x3 ? 3 : 1); ++part)                // hi.Ghi, lo.Ghi, hi.Glo
+                    for (int c = 0; c < nk; ++c) {
+                        const uint64_t bd = make_desc(smem_u32(gam + (size_t)(c + (part == 2 ? nk : 0)) * N * 128), 128);
+                        const uint32_t xa = tmem_base + (part == 1 ? 448u : 384u);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ts(tmem_base + 256u, tmem_base + 384u + (uint32_t)((c * 4 + kk) * 8),
-                                     bd + (uint64_t)(kk * 2), idesc, (uint32_t)(c | kk));
-                }
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16_ts(tmem_base + 256u, xa + (uint32_t)((c * 4 + kk) * 8),
+                                         bd + (uint64_t)(kk * 2), idesc, (uint32_t)(part | c | kk));
+                    }
                 umma_commit(&bars.norm_full);
                 umma_commit(&bars.xsq_empty);
             };
@@ -496,7 +503,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * 128u;
                 uint32_t accum = 0;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int kc = 0; kc < p.kv; ++kc) {
                     mbar_wait(&bars.a_full[sa], pa);
                     const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
                     for (int ky = 0; ky < 3; ++ky) {
@@ -540,7 +547,7 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int c_lo = team * per;
         const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint8_t *my_stage = stage + team * STAGE_BYTES;
-        EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr);
+        EpiCtx ctx = make_epi(p.out, p.res, p.gate, p.post, 0, p.out_scale != nullptr, p.x3 != 0);
         const bool staged = p.tma_store && per == 32;         // one 32-channel TMA store per team and tile
         bool store_pending = false;
         uint32_t it = 0;
@@ -563,14 +570,26 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     float v[16];
                     tmem_ld16(tl + buf * 128u + (uint32_t)j0, v);
                     uint32_t w[8];
+                    if (p.x3) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 b = *reinterpret_cast<const float4 *>(sbias + j0 + 4 * q);
-                        const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y, x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
-                        const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 * x0, x1 * x1);
-                        const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 * x2, x3 * x3);
-                        w[2 * q] = *reinterpret_cast<const uint32_t *>(&lo);
-                        w[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&hi);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b = *reinterpret_cast<const float4 *>(sbias + j0 + 4 * q);
+                            const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y, x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
+                            v[4 * q] = x0 * x0; v[4 * q + 1] = x1 * x1; v[4 * q + 2] = x2 * x2; v[4 * q + 3] = x3 * x3;
+                        }
+                        uint32_t wl[8];
+                        split16(v, w, wl);
+                        tmem_st8(tl + 448u + (uint32_t)(j0 >> 1), wl);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b = *reinterpret_cast<const float4 *>(sbias + j0 + 4 * q);
+                            const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y, x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 * x0, x1 * x1);
+                            const __nv_bfloat162 hi = __floats2bfloat162_rn(x2 * x2, x3 * x3);
+                            w[2 * q] = *reinterpret_cast<const uint32_t *>(&lo);
+                            w[2 * q + 1] = *reinterpret_cast<const uint32_t *>(&hi);
+                        }
                     }
                     tmem_st8(tl + 384u + (uint32_t)(j0 >> 1), w);
                 }
@@ -611,9 +630,14 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         for (int e = 0; e < 4; ++e) {
                             const float xx = v[4 * q + e] + bb[e];
                             const float t = nr[4 * q + e] + ee[e];
-                            float rs;                                           // MUFU.RSQ: 2^-22 relative, far below bf16
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
-                            v[4 * q + e] = inverse ? xx * (t * rs) : xx * rs;
+                            if (p.x3) {                                         // fp32-faithful mode: IEEE sqrt / division
+                                const float sq = sqrtf(t);
+                                v[4 * q + e] = inverse ? xx * sq : xx / sq;
+                            } else {
+                                float rs;                                       // MUFU.RSQ: 2^-22 relative, far below bf16
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+                                v[4 * q + e] = inverse ? xx * (t * rs) : xx * rs;
+                            }
                         }
                     }
                     if (staged) {
@@ -938,7 +962,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->kind != 0 || op->k != 3 || op->stride != 1) return -1;
     if (cin % 64 || cout % 16 || cout > 128) return -1;
     const bool gdn = op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN;
-    if (gdn && (x3 || (cout != 128 && cout != 64))) return -1;      // (x3 + GDN: generic kernel)
+    if (gdn && (cout != 128 && cout != 64)) return -1;
     if (op->in.dtype != (x3 ? AIVC_BF16X2 : AIVC_BF16) || op->in.pad < 1 || op->in.c_off % 8 || op->in.c_stride % 16) return -1;
     if (op->act_channels) return -1;
     const int tiles_x = ceil_div(op->out.w, TILE_W);
@@ -968,7 +992,8 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.b_bytes = (uint32_t)p.ncta * 128u;                       // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
-    const size_t gdn_bytes = gdn ? (size_t)cout * cout * 2 + 2 * STAGE_BYTES : 0;   // gamma + two more staging tiles
+    // conv + GDN: gamma + two more staging tiles; split-bf16: gamma [hi | lo], no staging tiles (generic stores)
+    const size_t gdn_bytes = gdn ? (x3 ? (size_t)cout * cout * 4 - 2 * STAGE_BYTES : (size_t)cout * cout * 2 + 2 * STAGE_BYTES) : 0;
     const size_t fixed = 1024 + (size_t)NA * a_slot + (size_t)2 * sub * STAGE_BYTES + gdn_bytes;
     // SUB = 1 aims at two CTAs per SM (<= 111 KB each) when two weight groups fit in that
     const size_t two_cta = 111 * 1024;
@@ -1019,8 +1044,9 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     g_aivc_kernel_class = gdn ? AIVC_KC_TC3_GDN : AIVC_KC_TC3;
     if (gdn) {
         CUtensorMap tmG;
-        cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cout};
-        cuuint64_t strides[1] = {(cuuint64_t)cout * 2};
+        const int gk = x3 ? 2 * cout : cout;                   // x3: gamma rows are [hi | lo]
+        cuuint64_t dims[2] = {(cuuint64_t)gk, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)gk * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)cout};
         if (encode_map(&tmG, (void *)op->gdn_gamma, 2, dims, strides, box, 128, "gamma/3x3")) return 1;
         const int grid = ntiles < sm_count ? ntiles : sm_count;

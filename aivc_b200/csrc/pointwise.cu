@@ -490,6 +490,11 @@ __global__ void space_to_depth_kernel(FMap in, FMap out) {
         uint4 *d = reinterpret_cast<uint4 *>((__nv_bfloat16 *)out.data + ((size_t)py * out.pitch + px) * out.c_stride +
                                              out.c_off + q * in.c);
         for (int v = 0; v < vec; ++v) d[v] = s[v];
+        if (in.dtype == AIVC_BF16X2) {                         // lo halves: same layout, half a pixel further
+            const uint4 *sl = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(s) + (in.c_stride >> 1));
+            uint4 *dl = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(d) + (out.c_stride >> 1));
+            for (int v = 0; v < vec; ++v) dl[v] = sl[v];
+        }
     }
 }
 
@@ -515,8 +520,9 @@ int col2im_tconv_run(const aivc_conv_op *op, cudaStream_t st) {
 int space_to_depth_run(const aivc_conv_op *op, cudaStream_t st) {
     g_aivc_kernel_class = AIVC_KC_S2D;
     const aivc_fmap &in = op->in, &out = op->out;
-    if (in.dtype != AIVC_BF16 || out.dtype != AIVC_BF16) AIVC_FAIL("space_to_depth: bf16 maps only");
-    if (in.c % 8 || in.c_off % 8 || in.c_stride % 8 || out.c_off % 8 || out.c_stride % 8)
+    if ((in.dtype != AIVC_BF16 && in.dtype != AIVC_BF16X2) || out.dtype != in.dtype) AIVC_FAIL("space_to_depth: (split) bf16 maps only");
+    const int al = in.dtype == AIVC_BF16X2 ? 16 : 8;           // split maps: both halves 16-byte aligned
+    if (in.c % 8 || in.c_off % 8 || in.c_stride % al || out.c_off % 8 || out.c_stride % al)
         AIVC_FAIL("space_to_depth: channel views must be 16-byte multiples");
     if (out.c != 4 * in.c || out.h != (in.h + 1) / 2 || out.w != (in.w + 1) / 2)
         AIVC_FAIL("space_to_depth: output must be ceil(h/2) x ceil(w/2) x 4c");

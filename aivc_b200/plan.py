@@ -304,7 +304,7 @@ class Plan:
             self.src.c = buf_c
         if cfg.tc:
             self._split_narrow_tconvs()
-            if in_embed is not None and cfg.s2d_first and cfg.precision == 'bf16':
+            if in_embed is not None and cfg.s2d_first:
                 self._space_to_depth_first_layer()
         last = self.stages[-1]
         self.out_c = self.dst.c
@@ -374,7 +374,7 @@ class Plan:
         for s in self.stages:
             if s.kind == 3:
                 s.engine = ENGINE_SIMT
-                s.src.dtype = s.dst.dtype = BF16
+                s.src.dtype = s.dst.dtype = self.cfg.act_dtype
                 continue
             if s.kind == 2:
                 s.engine = ENGINE_SIMT
