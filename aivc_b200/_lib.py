@@ -63,13 +63,14 @@ _SIGS = {
                                       C.POINTER(FMap), C.c_void_p]),
     'aivc_yuv420_pack16': (C.c_int, [C.c_void_p] * 9 + [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p]),
     'aivc_warp_blend': (C.c_int, [C.POINTER(FMap)] * 3 + [C.c_int, C.c_int] + [C.POINTER(FMap)] * 2
-                        + [C.c_void_p]),
+                        + [C.c_void_p, C.c_void_p]),
     'aivc_warp_blend_nchw': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
     'aivc_finalize_frame': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.POINTER(FMap), C.c_void_p]),
     'aivc_mu_sigma_nchw': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'aivc_quantize_latent': (C.c_int, [C.POINTER(FMap), C.POINTER(FMap), C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.POINTER(FMap), C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.POINTER(FMap), C.c_void_p, C.c_void_p]),
+    'aivc_pdf_prob': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     'aivc_laplace_scale': (C.c_int, [C.POINTER(FMap), C.c_int, C.c_void_p, C.c_void_p]),
     'aivc_laplace_window': (C.c_int, [C.POINTER(FMap), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'aivc_dequantize_latent': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p, C.POINTER(FMap),

@@ -60,7 +60,27 @@ def _section_bits(frame_bytes):
     return bits
 
 
+def _rate_z(cond_net, z_i16, device):
+    """Per-symbol rate estimate of the z latent, [1, C_z, h_z, w_z] bits: EntropyCoder(BallePdfEstim(z_hat))
+    (pdf_estimator.py:172-202, entropy_coder.py:25-30).  A few thousand symbols through a 1-3-3-3-1 MLP per
+    channel: evaluated by the (host-side) Balle mirror, like the z table."""
+    z = torch.from_numpy(z_i16.astype(np.float32))[None]
+    with torch.no_grad():
+        p = cond_net.pdf_z(z.to(next(cond_net.pdf_z.parameters()).device))
+    return (-torch.log2(torch.clamp(p.float(), 2.0 ** -16, 1.0))).to(device)
+
+
 def gop_forward(model, model_input, device=None, cfg=None):
+    """FullNet.GOP_forward (see the module docstring).  net_out[frame] holds, as the reference's encoder does:
+      x_hat                      reconstructed YUV420 dict (8-bit levels / 255)
+      code                       in_layer(raw frame), [1, 3, H, W]
+      alpha, beta                clamp(MOFNet channel 0 / 1 + 0.5, 0, 1) repeated to 3 channels (decode.py:731-739);
+                                 I frames: ones (decode.py:500-504); P frames: beta = 1
+      warping                    x_warp = beta w(prev, v_prev) + (1 - beta) w(next, v_next); I frames: zeros
+      mode_rate_y/z, codec_rate_y/z   per-symbol rate ESTIMATES in bits, [1, C, h, w] (pdf_estimator.py:27-70,
+                                 172-202; entropy_coder.py:25-30) -- what loss_function.py:158,186 sums; I frames
+                                 have no MOFNet latents: zeros
+      coded_bits                 (extra key) the REAL coded size of the four sections, from the bitstream"""
     gop = model_input['GOP_struct']
     name = model_input.get('GOP_struct_name') or ''
     raw = model_input['raw_frames']
@@ -72,25 +92,33 @@ def gop_forward(model, model_input, device=None, cfg=None):
     device = torch.device(device)
     codec = codec_for(model, h, w, device, cfg, idx_rate)
     frames = {f: _to_planes(raw[f], device) for f in gop}
-    bts, rec = codec.encode_gop(frames, gop)
+    aux = {}
+    bts, rec = codec.encode_gop(frames, gop, aux=aux)
 
     net_out = {}
     in_layer = model.in_layer
+    mnet, cnet = model.mode_net.mode_net, model.codec_net.codec_net
+    (hy, wy), _ = latent_dims(h, w)
     for f in gop:
-        mz, my, cz, cy = _section_bits(bts[f])
+        a = aux[f]
         x_hat = _to_yuv(rec[f], h, w)
         code = in_layer({k: (frames[f][i].view(1, 1, *x_hat[k].shape[2:]).float() / 255.)
                          for i, k in enumerate('yuv')})
-        is_i = gop[f]['type'] == FRAME_I
-        one = torch.ones((1, 3, h, w), device=device)
-        net_out[f] = {
-            'x_hat': x_hat, 'code': code,
-            # the fused pipeline does not materialise alpha / beta / the warped prediction; the
-            # values below are the I-frame constants (decode.py:500-504) -- they only feed logging
-            'alpha': one, 'beta': one, 'warping': code if is_i else in_layer(x_hat),
-            'mode_rate_y': torch.tensor([my], device=device), 'mode_rate_z': torch.tensor([mz], device=device),
-            'codec_rate_y': torch.tensor([cy], device=device), 'codec_rate_z': torch.tensor([cz], device=device),
-        }
+        out = {'x_hat': x_hat, 'code': code,
+               'codec_rate_y': a['codec_rate_y'].view(1, cnet.nb_ft_y, hy, wy),
+               'codec_rate_z': _rate_z(cnet, a['codec_keep']['z'], device),
+               'coded_bits': dict(zip(('mode_z', 'mode_y', 'codec_z', 'codec_y'), _section_bits(bts[f])))}
+        if gop[f]['type'] == FRAME_I:
+            one = torch.ones((1, 3, h, w), device=device)
+            out.update(alpha=one, beta=one, warping=torch.zeros((1, 3, h, w), device=device),
+                       mode_rate_y=torch.zeros((1, mnet.nb_ft_y, hy, wy), device=device),
+                       mode_rate_z=torch.zeros_like(out['codec_rate_z']))
+        else:
+            wa = a['warp'].view(5, h, w)
+            out.update(alpha=wa[0].expand(1, 3, h, w), beta=wa[1].expand(1, 3, h, w), warping=wa[2:5].unsqueeze(0),
+                       mode_rate_y=a['mode_rate_y'].view(1, mnet.nb_ft_y, hy, wy),
+                       mode_rate_z=_rate_z(mnet, a['mode_keep']['z'], device))
+        net_out[f] = out
 
     if model_input.get('generate_bitstream'):
         d = model_input.get('bitstream_dir') or './'
@@ -105,6 +133,40 @@ def gop_forward(model, model_input, device=None, cfg=None):
         with open(d + 'data_dim.pkl', 'wb') as fo:
             pickle.dump({'x': (h, w), 'y': dims_y, 'z': dims_z}, fo, pickle.HIGHEST_PROTOCOL)
     return net_out
+
+
+def compute_metrics_one_gop(net_out, target, nb_pad_frame=0):
+    """The logging half of compute_metrics_one_GOP (loss_function.py:103-257) on the device metrics kernel
+    (csrc/metrics.cu): per frame mse, psnr, ms_ssim, ms_ssim_db, mse_warping, psnr_warping, the three rates in bpp,
+    mean_alpha, mean_beta, h, w; plus the 'GOP' average (distortions over the real frames, rates over all --
+    average_N_frame, loss_function.py:260-339).  target: {'frame_i': YUV420 dict in [0, 1]}."""
+    from . import metrics
+    result = {}
+    for f in target:
+        o = net_out[f]
+        h, w = target[f]['y'].shape[2:]
+        dev = o['code'].device
+        m = metrics.frame_metrics(_to_planes(o['x_hat'], dev), _to_planes(target[f], dev), h, w)
+        npx = float(h * w)
+        r = {k: float(o[k].sum()) / npx for k in ('mode_rate_y', 'mode_rate_z', 'codec_rate_y', 'codec_rate_z')}
+        mse_w = float(((o['warping'] - o['code']) ** 2).mean())
+        result[f] = {'mse': m['mse'], 'psnr': m['psnr'], 'ms_ssim': m['ms_ssim'], 'ms_ssim_db': m['ms_ssim_db'],
+                     'mse_warping': mse_w, 'psnr_warping': 10 * np.log10(1. / max(mse_w, 1e-20)),
+                     'codec_rate_bpp': r['codec_rate_y'] + r['codec_rate_z'],
+                     'mode_rate_bpp': r['mode_rate_y'] + r['mode_rate_z'],
+                     'total_rate_bpp': sum(r.values()),
+                     'mean_alpha': float(o['alpha'].mean()), 'mean_beta': float(o['beta'].mean()), 'h': float(h), 'w': float(w)}
+    names = sorted(result, key=lambda f: int(f.split('_')[1]))
+    real = names[:len(names) - nb_pad_frame] if nb_pad_frame else names
+    gop = {}
+    for k in result[names[0]]:       # distortions over the real frames only, everything else over all frames
+        src = real if k in ('mse', 'mse_warping', 'ms_ssim', 'ms_ssim_db', 'psnr') else names
+        gop[k] = float(np.mean([result[f][k] for f in src]))
+    gop['psnr'] = 10 * np.log10(1. / max(gop['mse'], 1e-20))                 # of the average mse, not the average psnr
+    gop['psnr_warping'] = 10 * np.log10(1. / max(gop['mse_warping'], 1e-20))
+    gop['ms_ssim_db'] = -10.0 * np.log10(max(1. - gop['ms_ssim'], 1e-20))
+    result['GOP'] = gop
+    return result
 
 
 def encode_video(model, gops_of_frames, gop_name, h, w, device='cuda:0', cfg=None, idx_rate=0., idx_first=0):

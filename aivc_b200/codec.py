@@ -131,11 +131,12 @@ class CondNetEngine:
             self.gs_in.zero_channels(self.cy, self.gs_in.c)
 
     # ---------------------------------------------------------------- encoder
-    def encode_launch(self, sl, frame_type, use_shortcut, first_of_i_frame=False):
+    def encode_launch(self, sl, frame_type, use_shortcut, first_of_i_frame=False, rate=None):
         """Enqueue analysis, quantisation and synthesis; symbols / CDF bounds are copied to the
         pinned slot `sl` asynchronously.  No host synchronisation.  The shortcut transform g_a_ref does not
         depend on the analysis side, so it runs on a second stream next to g_a -> h_a -> h_s -> quantise and
-        fills the SMs those leave idle (wave tails, the latency-bound 68x120 stages); g_s joins both."""
+        fills the SMs those leave idle (wave tails, the latency-bound 68x120 stages); g_s joins both.
+        `rate`: optional fp32 device tensor [cy * hy * wy] receiving the per-symbol rate estimate in bits."""
         L, st = _lib.lib(), _lib.stream_ptr()
         enc_gain, dec_gain = self.gains[frame_type]
         main = torch.cuda.current_stream()
@@ -163,7 +164,8 @@ class CondNetEngine:
         yf, hsf, yh = self.g_a.out_fmap, self.h_s.out_fmap, self._yhat_view()
         _lib.check(L.aivc_quantize_latent(C.byref(yf), C.byref(hsf), dec_gain.data_ptr(),
                                           self.q_dev.data_ptr(), self.bounds_dev.data_ptr(),
-                                          self.nz_dev.data_ptr(), C.byref(yh), st))
+                                          self.nz_dev.data_ptr(), C.byref(yh),
+                                          None if rate is None else rate.data_ptr(), st))
         sl.bounds.copy_(self.bounds_dev, non_blocking=True)
         sl.nz.copy_(self.nz_dev, non_blocking=True)
         sl.event.record()
@@ -174,10 +176,13 @@ class CondNetEngine:
             self._shortcut(use_shortcut)
         self.g_s.run()
 
-    def encode_finish(self, sl):
-        """Host side (any thread): range-code the latent of slot `sl` -> two bitstream sections."""
+    def encode_finish(self, sl, keep=None):
+        """Host side (any thread): range-code the latent of slot `sl` -> two bitstream sections.
+        `keep`: optional dict that receives a copy of the z symbols (rate logging)."""
         sl.event.synchronize()
         (hy, wy), (hz, wz) = self.dims_y, self.dims_z
+        if keep is not None:
+            keep['z'] = sl.z.numpy().reshape(self.cz, hz, wz).copy()
         sec_z = entropy.encode_z(self.table, sl.z.numpy().reshape(self.cz, hz, wz))
         sec_y = entropy.encode_y(sl.bounds.numpy().view(np.uint32).reshape(self.cy, hy * wy),
                                  sl.nz.numpy())
@@ -318,14 +323,16 @@ class FrameCodec:
     def _zero_pred(self):
         self.codec_in.zero_channels(3, 6)
 
-    def _motion(self, frame_type):
+    def _motion(self, frame_type, aux=None):
+        """aux: optional fp32 device tensor [5, h, w] receiving alpha, beta and x_warp (3 planes, [0,1] units)."""
         L = _lib.lib()
         mo = self.mof.g_s.out_fmap
         prev, nxt = self.mof_in.view(3, 3), self.mof_in.view(6, 3)
         pred, skip = self.codec_in.view(3, 3), self.skip.view(0, 3)
         _lib.check(L.aivc_warp_blend(C.byref(mo), C.byref(prev), C.byref(nxt),
                                      1 if frame_type == FRAME_P else 0, 1 if self.levels else 0,
-                                     C.byref(pred), C.byref(skip), _lib.stream_ptr()))
+                                     C.byref(pred), C.byref(skip), None if aux is None else aux.data_ptr(),
+                                     _lib.stream_ptr()))
 
     def _finalize(self, frame_type, out_planes):
         cod = _lib.FMap.from_buffer_copy(self.codec.g_s.out_fmap)
@@ -375,12 +382,16 @@ class FrameCodec:
             self._finalize(frame_type, rec)
         return rec
 
-    def encode_gop(self, frames, gop):
+    def encode_gop(self, frames, gop, aux=None):
         """frames: {'frame_i': (y,u,v) device planes}. Returns ({name: bytes}, {name: planes}).
         The GPU runs ahead through the whole GOP; the serial range coder of every latent runs on
-        host worker threads as soon as its symbols have landed in pinned memory."""
+        host worker threads as soon as its symbols have landed in pinned memory.
+        aux: optional dict; filled per frame with what the reference's encoder logs (loss_function.py:158-204):
+        'mode_rate_y' / 'codec_rate_y' (fp32 [cy, hy, wy] device tensors, bits per symbol), 'mode_z' / 'codec_z'
+        (int16 numpy symbols, for the z rate) and 'warp' (fp32 [5, h, w]: alpha, beta, x_warp; inter frames)."""
         pool = self._pool()
         rec, futs = {}, {}
+        f32 = dict(dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             for i, f in enumerate(coding_order(gop)):
                 e = gop[f]
@@ -399,13 +410,22 @@ class FrameCodec:
                     if not fused:
                         self._pack(frames[f], self.mof_in, 0)
                         self._refs(ft, prev_r, next_r)
+                a = None
+                if aux is not None:
+                    a = aux[f] = {'mode_keep': {}, 'codec_keep': {},
+                                  'codec_rate_y': torch.empty(self.codec.n_y, **f32)}
+                    if ft != FRAME_I:
+                        a['mode_rate_y'] = torch.empty(self.mof.n_y, **f32)
+                        a['warp'] = torch.empty(5 * self.h * self.w, **f32)
+                if ft != FRAME_I:
                     sl = self.mof.slot(i)
-                    self.mof.encode_launch(sl, ft, ft == FRAME_B)
-                    parts.append(pool.submit(self.mof.encode_finish, sl))
-                    self._motion(ft)
+                    self.mof.encode_launch(sl, ft, ft == FRAME_B, rate=a and a['mode_rate_y'])
+                    parts.append(pool.submit(self.mof.encode_finish, sl, a and a['mode_keep']))
+                    self._motion(ft, a and a['warp'])
                 sl = self.codec.slot(i)
-                self.codec.encode_launch(sl, ft, ft != FRAME_I, first_of_i_frame=(ft == FRAME_I))
-                parts.append(pool.submit(self.codec.encode_finish, sl))
+                self.codec.encode_launch(sl, ft, ft != FRAME_I, first_of_i_frame=(ft == FRAME_I),
+                                         rate=a and a['codec_rate_y'])
+                parts.append(pool.submit(self.codec.encode_finish, sl, a and a['codec_keep']))
                 rec[f] = self.new_planes()
                 self._finalize(ft, rec[f])
                 futs[f] = parts

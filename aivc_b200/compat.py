@@ -20,11 +20,12 @@ from . import layers as L, models as M
 
 _MODULE_MAP = {
     'layers.misc.custom_conv_layers': ('ChengResBlock', 'ResBlock', 'CustomConvLayer', 'UpscalingLayer'),
-    'layers.misc.misc_layers': ('GDN', 'Quantizer', 'PdfParamParameterizer'),
+    'layers.misc.misc_layers': ('GDN', 'Quantizer', 'PdfParamParameterizer', 'View', 'LowerBound'),
     'layers.misc.attention': ('AttentionResBlock', 'SimplifiedAttention'),
     'layers.ae.ae_layers': ('InputLayer', 'OutputLayer'),
     'layers.multi_rate.gain_matrix': ('GainMatrix',),
-    'layers.entropy_coding.pdf_estimator': ('BallePdfEstim',),
+    'layers.entropy_coding.pdf_estimator': ('BallePdfEstim', 'ParametricPdf'),
+    'layers.entropy_coding.entropy_coder': ('EntropyCoder',),
 }
 
 

@@ -95,3 +95,17 @@ AIVC_HD uint32_t aivc_laplace_cdf_int(float b, int i) {
     const float scaled = rintf(AIVC_FMULF(cdf, AIVC_CDF_SCALE));
     return ((uint32_t)(int32_t)scaled + (uint32_t)i) & 0xFFFFu;
 }
+
+// fp32 Laplace(0, b) CDF at t (torch.distributions.Laplace.cdf: 0.5 - 0.5 sign(t) expm1(-|t| / b)) and the rate
+// estimate of an integer symbol q in bits (pdf_estimator.py:27-70 with zero_mu, entropy_coder.py:25-30):
+// -log2 clamp(cdf(q + 1/2) - cdf(q - 1/2), 2^-16, 1).
+AIVC_HD float aivc_laplace_cdf_f(float b, float t) {
+    const float x = AIVC_FDIV(-fabsf(t), b);
+    const float e = (float)aivc_expm1_neg((double)x);
+    const float hs = t < 0.f ? -0.5f : (t > 0.f ? 0.5f : 0.f);
+    return AIVC_FSUBF(0.5f, AIVC_FMULF(hs, e));
+}
+AIVC_HD float aivc_laplace_rate_bits(float b, float q) {
+    const float p = AIVC_FSUBF(aivc_laplace_cdf_f(b, AIVC_FADDF(q, 0.5f)), aivc_laplace_cdf_f(b, AIVC_FSUBF(q, 0.5f)));
+    return -log2f(fminf(fmaxf(p, 1.52587890625e-05f), 1.0f));
+}

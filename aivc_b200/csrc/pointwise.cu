@@ -179,7 +179,7 @@ __device__ __forceinline__ float bilerp_sample(const Bilerp &b, int w, int h, L 
 }
 
 __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p, FMap pred,
-                                  FMap skip, int levels) {
+                                  FMap skip, int levels, float *__restrict__ aux) {
     const int h = pred.h, w = pred.w;
     const size_t n = (size_t)h * w;
     // both references are channel slices 3..5 / 6..8 of ONE 16-channel bf16 pixel buffer (the bf16 engine's mof_in)
@@ -237,7 +237,9 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
             fm_store(pred, y, x, ch, xw * alpha);             // warped_ref * alpha  (decode.py:542)
             if (levels) xw /= 255.f;
             fm_store(skip, y, x, ch, (1.f - alpha) * xw);     // (1 - alpha) * warped (decode.py:536)
+            if (aux) aux[(size_t)(2 + ch) * n + i] = xw;
         }
+        if (aux) { aux[i] = alpha; aux[n + i] = beta; }
     }
 }
 
@@ -334,7 +336,7 @@ __global__ void mu_sigma_nchw_kernel(const float *__restrict__ hs, float *__rest
 
 __global__ void quantize_latent_kernel(FMap y, FMap hs, const float *__restrict__ dec_gain,
                                        int16_t *__restrict__ q, uint32_t *__restrict__ bounds,
-                                       int32_t *__restrict__ nz, FMap yhat) {
+                                       int32_t *__restrict__ nz, FMap yhat, float *__restrict__ rate) {
     const int c = y.c, hw = y.h * y.w;
     const size_t n = (size_t)c * hw;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -353,6 +355,25 @@ __global__ void quantize_latent_kernel(FMap y, FMap hs, const float *__restrict_
         bounds[o] = lo | (hi << 16);
         if (qi != 0) nz[ch] = 1;
         if (yhat.data) fm_store(yhat, yy, xx, ch, (qf + mu) * dec_gain[ch]);
+        if (rate) rate[o] = aivc_laplace_rate_bits(b, qf);
+    }
+}
+
+__global__ void pdf_prob_kernel(const float *__restrict__ y, const float *__restrict__ mu,
+                                const float *__restrict__ sigma, int family, int accumulate,
+                                float *__restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float m = mu ? mu[i] : 0.f, s = sigma[i];
+        const float up = (y[i] + 0.5f) - m, dn = (y[i] - 0.5f) - m;
+        float p;
+        if (family == 0) {
+            const float b = aivc_laplace_scale(s);
+            p = aivc_laplace_cdf_f(b, up) - aivc_laplace_cdf_f(b, dn);
+        } else {                                   // torch.distributions.Normal.cdf: 0.5 (1 + erf((x - mu) / (sigma sqrt 2)))
+            const float r = 1.f / (s * 1.41421356237309504880f);
+            p = 0.5f * (1.f + erff(up * r)) - 0.5f * (1.f + erff(dn * r));
+        }
+        out[i] = accumulate ? out[i] + p : p;
     }
 }
 
@@ -623,7 +644,7 @@ int aivc_yuv420_pack16(const void *y0, const void *u0, const void *v0, const voi
 
 int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
                     int frame_is_p, int levels, const aivc_fmap *pred, const aivc_fmap *skip,
-                    void *stream) {
+                    float *aux, void *stream) {
     if (validate_fmap(mof, "warp mof") || validate_fmap(prev, "warp prev") ||
         validate_fmap(next, "warp next") || validate_fmap(pred, "warp pred") ||
         validate_fmap(skip, "warp skip"))
@@ -633,7 +654,7 @@ int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap
     if (prev->h != pred->h || prev->w != pred->w || next->h != pred->h || next->w != pred->w)
         AIVC_FAIL("warp_blend: reference / prediction size mismatch");
     warp_blend_kernel<<<grid_for((size_t)pred->h * pred->w), PT, 0, (cudaStream_t)stream>>>(
-        to_dev(*mof), to_dev(*prev), to_dev(*next), frame_is_p, to_dev(*pred), to_dev(*skip), levels);
+        to_dev(*mof), to_dev(*prev), to_dev(*next), frame_is_p, to_dev(*pred), to_dev(*skip), levels, aux);
     AIVC_CHECK_LAUNCH("warp_blend");
     return 0;
 }
@@ -679,7 +700,7 @@ int aivc_mu_sigma_nchw(const float *hs, float *mu, float *sigma, int c, int hw, 
 }
 
 int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *dec_gain, int16_t *q,
-                         uint32_t *bounds, int32_t *nz, const aivc_fmap *yhat, void *stream) {
+                         uint32_t *bounds, int32_t *nz, const aivc_fmap *yhat, float *rate, void *stream) {
     if (validate_fmap(y, "quantize y") || validate_fmap(hs, "quantize hs")) return 1;
     if (hs->c < 2 * y->c || hs->h < y->h || hs->w < y->w)
         AIVC_FAIL("quantize_latent: hyper-decoder output must be >= 2C channels and cover y");
@@ -690,8 +711,17 @@ int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *d
         yh = to_dev(*yhat);
     }
     quantize_latent_kernel<<<grid_for((size_t)y->c * y->h * y->w), PT, 0, (cudaStream_t)stream>>>(
-        to_dev(*y), to_dev(*hs), dec_gain, q, bounds, nz, yh);
+        to_dev(*y), to_dev(*hs), dec_gain, q, bounds, nz, yh, rate);
     AIVC_CHECK_LAUNCH("quantize_latent");
+    return 0;
+}
+
+int aivc_pdf_prob(const float *y, const float *mu, const float *sigma, int family, int accumulate, float *out,
+                  size_t n, void *stream) {
+    if (!y || !sigma || !out) AIVC_FAIL("pdf_prob: null tensor");
+    if (family != 0 && family != 1) AIVC_FAIL("pdf_prob: family %d (0 = laplace, 1 = normal)", family);
+    pdf_prob_kernel<<<grid_for(n), PT, 0, (cudaStream_t)stream>>>(y, mu, sigma, family, accumulate, out, n);
+    AIVC_CHECK_LAUNCH("pdf_prob");
     return 0;
 }
 

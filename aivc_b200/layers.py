@@ -172,21 +172,88 @@ class Quantizer(nn.Module):
 
 
 class PdfParamParameterizer(nn.Module):
-    """Splits the hyper-decoder output into mu / sigma (misc_layers.py:180-269).
-    Only the single-component mode AIVC ships is implemented."""
+    """Splits the hyper-decoder output into the parameters of a K-component mixture (misc_layers.py:180-269):
+    channels [mu_0..mu_K-1 | log var_0.. | (log gamma_0.. if 'gamma') | weight logits_1..K-1], sigma =
+    exp(0.5 clamp(log var, LOG_VAR_MIN, LOG_VAR_MAX)), weights = softmax over (1, logits).  AIVC ships K = 1."""
 
     def __init__(self, ec_mode, nb_ft):
         super().__init__()
         self.ec_mode, self.nb_ft = ec_mode, nb_ft
-        toks = ec_mode.split('_')
-        if 'two' in toks or 'three' in toks or 'gamma' in toks:
-            raise NotImplementedError('mixture entropy models are not used by AIVC inference')
 
     def forward(self, x):
         from . import ops
-        mu, sigma = ops.mu_sigma(x, self.nb_ft)
-        return [{'mu': mu, 'sigma': sigma,
-                 'gamma': torch.ones_like(mu), 'weight': torch.ones_like(mu)}]
+        toks = self.ec_mode.split('_')
+        K = 2 if 'two' in toks else (3 if 'three' in toks else 1)
+        C = self.nb_ft
+        if K == 1 and 'gamma' not in toks:
+            mu, sigma = ops.mu_sigma(x, C)
+            return [{'mu': mu, 'sigma': sigma, 'gamma': torch.ones_like(mu), 'weight': torch.ones_like(mu)}]
+        sl = lambda i: x[:, i * C:(i + 1) * C]
+        comp = [ops.mu_sigma(torch.cat((sl(k), sl(K + k)), 1), C) for k in range(K)]
+        pos = 2 * K
+        gammas = []
+        for k in range(K):
+            if 'gamma' in toks:
+                gammas.append(ops.mu_sigma(torch.cat((sl(pos), sl(pos)), 1), C)[1])
+                pos += 1
+            else:
+                gammas.append(torch.ones_like(comp[k][0]))
+        w = torch.stack([torch.ones_like(comp[0][0])] + [sl(pos + k - 1).float() for k in range(1, K)], 1)
+        w = torch.softmax(w, dim=1)
+        return [{'mu': comp[k][0], 'sigma': comp[k][1], 'gamma': gammas[k], 'weight': w[:, k]} for k in range(K)]
+
+
+class ParametricPdf(nn.Module):
+    """P(y) = sum over components of cdf(y + 1/2) - cdf(y - 1/2), Laplace(mu, sigma / sqrt 2) or Normal(mu, sigma)
+    (pdf_estimator.py:17-70; like the reference, component weights are NOT applied here)."""
+
+    def __init__(self, pdf_family):
+        super().__init__()
+        self.pdf_family = pdf_family
+
+    def forward(self, y_tilde, all_pdf_param, zero_mu=False):
+        from . import ops
+        toks = self.pdf_family.split('_')
+        family = 'normal' if 'normal' in toks else 'laplace'
+        out = None
+        for prm in all_pdf_param:
+            mu = None if ('mu' in toks or zero_mu) else prm.get('mu')
+            out = ops.pdf_prob(y_tilde, mu, prm.get('sigma'), family, out)
+        return out.view_as(y_tilde)
+
+
+class EntropyCoder(nn.Module):
+    """rate = -log2 clamp(p, 2^-16, 1)   (entropy_coder.py:18-30)"""
+
+    def forward(self, prob_x, x=None):
+        return -torch.log2(torch.clamp(prob_x, 2.0 ** -16, 1.0))
+
+
+class View(nn.Module):
+    """misc_layers.py:30-36 (appears in pickled models; pure reshape)"""
+
+    def __init__(self, shape):
+        super().__init__()
+        self.shape = shape
+
+    def forward(self, x):
+        return x.view(*self.shape)
+
+
+class LowerBound(torch.autograd.Function):
+    """max(inputs, bound) with the pass-through gradient of misc_layers.py:39-60 (GDN's reparametrisation; the
+    inference path folds it into the packed GDN parameters, plan._gdn_params)."""
+
+    @staticmethod
+    def forward(ctx, inputs, bound):
+        b = torch.ones_like(inputs) * bound
+        ctx.save_for_backward(inputs, b)
+        return torch.max(inputs, b)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        inputs, b = ctx.saved_tensors
+        return ((inputs >= b) | (grad_output < 0)).type(grad_output.dtype) * grad_output, None
 
 
 class InputLayer(nn.Module):

@@ -22,7 +22,7 @@ from torch import nn
 
 from .layers import (CustomConvLayer, UpscalingLayer, ChengResBlock, SimplifiedAttention,
                      PdfParamParameterizer, InputLayer, OutputLayer, GainMatrix, BallePdfEstim,
-                     Quantizer)
+                     Quantizer, ParametricPdf, EntropyCoder)
 
 FRAME_I, FRAME_P, FRAME_B = 0, 1, 2      # func_util/GOP_structure.py:23-25
 
@@ -69,14 +69,6 @@ def hyper_synthesis(Cz, C, Cy):
         CustomConvLayer(3, C, 2 * Cy, non_linearity='no'))
 
 
-class ParametricPdfStub(nn.Module):
-    """Holder for ``pdf_y``; the Laplace rate itself is evaluated by the fused
-    quantise kernel (pdf_estimator.py:27-70 semantics)."""
-
-    def __init__(self, pdf_family='laplace'):
-        super().__init__()
-        self.pdf_family = pdf_family
-
 
 class ConditionalNet(nn.Module):
     def __init__(self, in_c, ref_c, out_c, C=128, Cy=64, Cz=64, Csc=64):
@@ -88,7 +80,8 @@ class ConditionalNet(nn.Module):
         self.h_a = hyper_analysis(Cy, C, Cz)
         self.h_s = hyper_synthesis(Cz, C, Cy)
         self.g_s = synthesis(Cy + Csc, C, out_c)
-        self.pdf_y = ParametricPdfStub('laplace')
+        self.pdf_y = ParametricPdf('laplace')     # (inside the codec the fused quantise kernel evaluates the same rate)
+        self.entropy_coder = EntropyCoder()
         self.pdf_z = BallePdfEstim(Cz, pdf_family='')
         self.pdf_parameterizer = PdfParamParameterizer('laplace', Cy)
         self.quantizer = Quantizer()

@@ -38,6 +38,22 @@ def mu_sigma(x, nb_ft):
     return mu, sigma
 
 
+def pdf_prob(y, mu, sigma, family, out=None):
+    """One component of ParametricPdf.forward (pdf_estimator.py:27-70): cdf(y + 1/2) - cdf(y - 1/2);
+    `out` given: accumulate into it."""
+    _need_cuda(y, sigma)
+    y, sigma = y.contiguous().float(), sigma.contiguous().float()
+    mu = None if mu is None else mu.contiguous().float()
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().aivc_pdf_prob(y.data_ptr(), None if mu is None else mu.data_ptr(), sigma.data_ptr(),
+                                            {'laplace': 0, 'normal': 1}[family], 1 if acc else 0, out.data_ptr(),
+                                            y.numel(), _lib.stream_ptr()))
+    return out
+
+
 def yuv420_to_444(y, u, v):
     """InputLayer.forward (ae_layers.py:27-35) -> [1,3,H,W]."""
     _need_cuda(y, u, v)

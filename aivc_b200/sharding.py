@@ -25,28 +25,76 @@ def gather_gop_bytes(mine, n_gops):
 
 
 # ------------------------------------------------------------------------------------------
-# Frame-level sharding inside ONE GOP (latency mode): frames of the same dependency level are
-# independent given the reconstructions of earlier levels (gop.levels), so a level's frames are
-# dealt round-robin to the ranks and every new reconstruction is broadcast (NCCL over NVLink:
-# 3.1 MB of 8-bit 4:2:0 planes per 1080p frame) before the next level starts.  For '1_GOP_32'
-# on 8 GPUs the critical path is 1+1+1+1+1+1+2 = 8 frame times instead of 33.
-def _bcast_planes(planes, shapes, src, device):
+# Frame-level sharding inside ONE GOP (latency mode; BASELINE.json configs[3]): frames of the same
+# dependency level are independent given the reconstructions of earlier levels (gop.levels;
+# func_util/GOP_structure.py:27-67 is the recursion that creates the levels, real_life/decode.py:119-121,
+# 246-249 the serial loop this parallelises), so a level's frames are dealt round-robin to the ranks and
+# every new 8-bit reconstruction -- exactly what the reference keeps as its references, decode.py:287-289 --
+# is broadcast (NCCL over NVLink: 3.1 MB of 4:2:0 planes per 1080p frame) before the next level starts.
+# For '1_GOP_32' on 8 GPUs the critical path is 1+1+1+1+1+1+2 = 8 frame times instead of 33.
+# Every frame is coded by exactly one rank with the same kernels in the same order as in the serial
+# schedule, so the bitstream is byte-identical for any number of ranks.
+def _rank_world(rank, world):
+    if rank is None or world is None:
+        on = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    return rank, world
+
+
+def _exchange_level(level, local, rec, sizes, world, device, stats):
+    """Broadcast the reconstructions of `level` (frame i owned by rank i % world) to every rank."""
     import torch
-    flat = torch.cat([p.reshape(-1) for p in planes]) if planes is not None else \
-        torch.empty(sum(shapes), dtype=torch.uint8, device=device)
-    dist.broadcast(flat, src=src)
-    out, pos = [], 0
-    for n in shapes:
-        out.append(flat[pos:pos + n])
-        pos += n
-    return tuple(out)
+    if world == 1:
+        rec.update(local)
+        return
+    ev = None
+    if stats is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if device.type == 'cuda' else None
+        if ev:
+            ev[0].record()
+    flats, works = [], []
+    for i, f in enumerate(level):
+        flat = torch.cat([p.reshape(-1) for p in local[f]]) if f in local else \
+            torch.empty(sum(sizes), dtype=torch.uint8, device=device)
+        works.append(dist.broadcast(flat, src=i % world, async_op=True))
+        flats.append(flat)
+    for w in works:
+        w.wait()
+    for f, flat in zip(level, flats):
+        out, pos = [], 0
+        for n in sizes:
+            out.append(flat[pos:pos + n])
+            pos += n
+        rec[f] = tuple(out)
+    if stats is not None:
+        stats['bcasts'] = stats.get('bcasts', 0) + len(level)
+        if ev:
+            ev[1].record()
+            stats.setdefault('_events', []).append(ev)
 
 
-def encode_gop_frame_parallel(codec, frames, gop_struct, plane_sizes, device):
-    """Every rank holds all source frames of the GOP.  Returns (bytes per frame on rank 0 / None
-    elsewhere, reconstructions of all frames on every rank)."""
+def _close_stats(stats):
+    if stats is None:
+        return
+    import torch
+    evs = stats.pop('_events', [])
+    if evs:
+        torch.cuda.synchronize()
+        stats['bcast_s'] = stats.get('bcast_s', 0.0) + sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+
+def _plane_sizes(codec):
+    hc, wc = (codec.h + 1) // 2, (codec.w + 1) // 2
+    return (codec.h * codec.w, hc * wc, hc * wc)
+
+
+def encode_gop_frame_parallel(codec, frames, gop_struct, rank=None, world=None, stats=None):
+    """Every rank holds all source frames of the GOP ({'frame_i': (y, u, v) uint8 device planes}).
+    Returns ({'frame_i': bytes}, {'frame_i': planes}) -- the complete GOP on EVERY rank (the per-frame byte strings
+    are all-gathered: KB..MB), so that any rank can assemble the container or decode."""
     from .gop import levels
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world(rank, world)
+    sizes = _plane_sizes(codec)
     rec, mine = {}, {}
     for level in levels(gop_struct):
         local = {}
@@ -55,22 +103,23 @@ def encode_gop_frame_parallel(codec, frames, gop_struct, plane_sizes, device):
                 e = gop_struct[f]
                 mine[f], local[f] = codec.encode_frame(frames[f], e['type'], rec.get(e['prev_ref']),
                                                        rec.get(e['next_ref']))
-        for i, f in enumerate(level):           # one broadcast per new reference
-            rec[f] = _bcast_planes(local.get(f), plane_sizes, i % world, device)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(mine, gathered, dst=0)
-    if rank != 0:
-        return None, rec
+        _exchange_level(level, local, rec, sizes, world, codec.device, stats)
+    _close_stats(stats)
+    if world == 1:
+        return mine, rec
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
     merged = {}
     for d in gathered:
         merged.update(d)
     return merged, rec
 
 
-def decode_gop_frame_parallel(codec, frame_bytes, gop_struct, plane_sizes, device):
-    """frame_bytes: {'frame_i': bytes} on every rank. Returns all reconstructions on every rank."""
+def decode_gop_frame_parallel(codec, frame_bytes, gop_struct, rank=None, world=None, stats=None):
+    """frame_bytes: {'frame_i': bytes} on every rank.  Returns all reconstructions on every rank."""
     from .gop import levels
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world(rank, world)
+    sizes = _plane_sizes(codec)
     rec = {}
     for level in levels(gop_struct):
         local = {}
@@ -79,6 +128,6 @@ def decode_gop_frame_parallel(codec, frame_bytes, gop_struct, plane_sizes, devic
                 e = gop_struct[f]
                 local[f] = codec.decode_frame(frame_bytes[f], e['type'], rec.get(e['prev_ref']),
                                               rec.get(e['next_ref']))
-        for i, f in enumerate(level):
-            rec[f] = _bcast_planes(local.get(f), plane_sizes, i % world, device)
+        _exchange_level(level, local, rec, sizes, world, codec.device, stats)
+    _close_stats(stats)
     return rec

@@ -108,36 +108,54 @@ def peaks():
 
 # ------------------------------------------------------------------------------ reference arm
 def cpu_reference_sample(budget_s, threads=None):
-    """Times the oracle (CPU restatement of the reference's algorithm, fp32 torch on host cores)
-    on a bounded sample: encode + decode of the GOP's I frame, on a full-width crop of the 1080p
-    frame whose height is fitted to `budget_s`.  Conv cost is linear in area, so
-    frames/s at 1080p = (crop_rows / 1080) / seconds."""
+    """Times the oracle (CPU restatement of the reference's algorithm, fp32 torch on host cores) on a bounded
+    sample of the benchmarked workload: ONE frame of every type -- I, P and B ('1_GOP_2') -- encoded AND decoded on a
+    full-width crop of the 1080p clip whose height is fitted to `budget_s`.  The GOP figure is composed by
+    frame-type counts (1_GOP_32 = 1 I + 1 P + 31 B) and scaled by area (the convolutions, >95 % of the time, are
+    linear in area):  frames/s at 1080p = 33 / ((t_I + t_P + 31 t_B) * 1080 / rows)."""
     import torch
-    from aivc_b200 import models
+    from aivc_b200 import models, gop as G
     from oracle import codec_ref as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     net = models.build_standin(**MODEL)
     tables = O.Tables(net)
+    gop = G.generate_gop_struct('1_GOP_2')
+    order = sorted(gop, key=lambda f: gop[f]['coding_order'])
 
     def run(rows):
-        fr = synth_gop(0, 1, rows, W)[0]
-        yuv = {k: torch.from_numpy(p.astype(np.float32) / 255.)[None, None] for k, p in zip('yuv', fr)}
-        z = O.zero_yuv(rows, W)
-        t0 = time.time()
-        data, rec, _ = O.encode_frame(net, tables, yuv, z, z, 0)
-        dec, _ = O.decode_frame(net, tables, data, z, z, 0, rows, W)
-        dt = time.time() - t0
-        assert all(torch.equal(rec[k], dec[k]) for k in 'yuv')
-        return dt
+        clip = synth_gop(0, 3, rows, W)
+        yuv = {'frame_%d' % i: {k: torch.from_numpy(p.astype(np.float32) / 255.)[None, None] for k, p in zip('yuv', fr)}
+               for i, fr in enumerate(clip)}
+        t = {0: 0.0, 1: 0.0, 2: 0.0}
+        rec, dec, bts = {}, {}, {}
+        for f in order:                                  # encoder (closed loop), frame by frame
+            ft = gop[f]['type']
+            prev = rec[gop[f]['prev_ref']] if ft != 0 else O.zero_yuv(rows, W)
+            nxt = rec[gop[f]['next_ref']] if ft == 2 else O.zero_yuv(rows, W)
+            t0 = time.time()
+            bts[f], rec[f], _ = O.encode_frame(net, tables, yuv[f], prev, nxt, ft)
+            t[ft] += time.time() - t0
+        for f in order:                                  # decoder
+            ft = gop[f]['type']
+            prev = dec[gop[f]['prev_ref']] if ft != 0 else O.zero_yuv(rows, W)
+            nxt = dec[gop[f]['next_ref']] if ft == 2 else O.zero_yuv(rows, W)
+            t0 = time.time()
+            dec[f], _ = O.decode_frame(net, tables, bts[f], prev, nxt, ft, rows, W)
+            t[ft] += time.time() - t0
+            assert all(torch.equal(rec[f][k], dec[f][k]) for k in 'yuv')
+        return t
 
-    t_probe = run(64)                               # calibration crop (also the warm-up)
-    rows = int(min(H, max(64, (budget_s / max(t_probe, 1e-3)) * 64)) // 8 * 8)
-    dt = run(rows)
-    fps = (rows / H) / dt
-    return fps, threads, ('I-frame encode+decode of a %dx%d crop of the 1080p frame (%.1f s), scaled by '
-                          'area to 1080p; inter frames cost ~2.9x more FLOPs, so this flatters the CPU'
-                          % (W, rows, dt))
+    probe_rows = 32
+    tp = run(probe_rows)                            # calibration crop (also the warm-up)
+    per_row = sum(tp.values()) / probe_rows
+    rows = int(min(H, max(32, budget_s / max(per_row, 1e-4))) // 16 * 16)
+    t = run(rows)
+    gop_s = (t[0] + t[1] + 31.0 * t[2]) * (H / rows)
+    fps = 33.0 / gop_s
+    return fps, threads, ('I, P and B frame (1_GOP_2) encode+decode of a %dx%d crop of the 1080p clip: %.2f / %.2f / %.2f s; '
+                          'GOP of 33 frames = t_I + t_P + 31 t_B = %.0f s after scaling by area (x %.2f)'
+                          % (W, rows, t[0], t[1], t[2], gop_s, H / rows)), gop_s
 
 
 def run_reference(args):
@@ -145,39 +163,220 @@ def run_reference(args):
     if rank != 0:
         return
     n_steps = args.steps + args.warmup
-    budget = max(2.0, min(20.0, 150.0 / max(n_steps, 1)))
-    vals, sample, threads = [], '', None
+    budget = max(3.0, min(40.0, 170.0 / max(n_steps, 1)))
+    vals, gops, sample, threads = [], [], '', None
     for i in range(n_steps):
-        fps, threads, sample = cpu_reference_sample(budget)
+        fps, threads, sample, gop_s = cpu_reference_sample(budget)
         if i >= args.warmup:
             vals.append(fps)
+            gops.append(gop_s)
     v = float(np.mean(vals))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / v * 33, 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.gpus),
+        'note': 'each step is a bounded SAMPLE of the workload (see cpu_baseline.sample): one frame of every type on a '
+                'crop, composed to a GOP by frame-type counts and scaled by area; a whole 1080p GOP takes '
+                '%.0f s on these cores, so ms_per_step of the full step is not measured (extrapolated: %.0f ms)'
+                % (float(np.mean(gops)), 1e3 * float(np.mean(gops))),
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, sharding='gop'):
     return {'workload': 'Random Access %s (33 frames/GOP), synthetic 1920x1080 YUV420, stand-in AIVC model '
                         '(MOFNet+CodecNet, C=128, Cy=Cz=64, seed 1234); 1 GOP per GPU per step' % GOP_NAME,
             'frames_per_step_per_gpu': 33, 'gop': GOP_NAME, 'resolution': '1920x1080',
-            'sharding': 'one GOP per rank, no data-path collective',
+            'sharding': 'one GOP per rank, no data-path collective' if sharding == 'gop' else
+                        'frames of one GOP dealt over the ranks by dependency level, NCCL broadcast of every new 8-bit reconstruction',
             'l2': 'working set per step (activations > 2 GB, 102 MB of frames) exceeds the 126 MB L2'}
 
 
+# ------------------------------------------------------------------------------ library baseline on the same GPU
+def gpu_library_baseline(dev):
+    """The reference graph in eager PyTorch (cuDNN / cuBLAS kernels) ON THIS GPU: g_a and g_s of the CodecNet stand-in
+    at 1080p through the oracle's torch.nn.functional restatement, fp32 (TF32 convolutions allowed) and bf16 --
+    SURVEY.md 2.2's second bar ("the reference GPU path").  Bench-leg use of oracle/."""
+    import copy
+    import torch
+    from aivc_b200 import models
+    from oracle import nn_ref as R
+    net = models.build_standin(**MODEL).codec_net.codec_net
+
+    def to_dev(m, dtype):
+        m = copy.deepcopy(m).to(dev).to(dtype)
+        for sub in m.modules():
+            if type(sub).__name__ == 'GDN':             # plain tensor attributes, not buffers (misc_layers.py:78-111)
+                for a in ('beta_bound', 'gamma_bound', 'pedestal'):
+                    setattr(sub, a, getattr(sub, a).to(dev).to(dtype))
+        return m
+
+    def time_ms(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    cases = {'g_a': (net.g_a, (1, 6, H, W)), 'g_s': (net.g_s, (1, net.nb_ft_y + net.out_c_shortcut_y, 68, 120))}
+    with torch.no_grad():
+        for name, (mod, shape) in cases.items():
+            for label, dtype in (('fp32_tf32', torch.float32), ('bf16', torch.bfloat16)):
+                m = to_dev(mod, dtype)
+                x = torch.rand(shape, device=dev).to(dtype)
+                out['%s_%s_ms' % (name, label)] = time_ms(lambda: R.forward_module(m, x))
+    return out
+
+
 # ------------------------------------------------------------------------------ CUDA arm
+class Arm:
+    """One FrameCodec + the timed legs of the benchmark on it."""
+
+    def __init__(self, precision, net, gop, names, host, resident, out_host, dev, world, rank, local, args):
+        import torch
+        from aivc_b200 import _lib
+        from aivc_b200.codec import FrameCodec
+        from aivc_b200.plan import Config
+        self.torch, self.L, self._lib = torch, _lib.lib(), _lib
+        self.codec = FrameCodec(net, H, W, dev, Config(precision=precision))
+        self.precision, self.gop, self.names = precision, gop, names
+        self.host, self.resident, self.out_host, self.dev = host, resident, out_host, dev
+        self.world, self.rank, self.local, self.args = world, rank, local, args
+        self.state = {}
+
+    def step(self, e2e):
+        torch, codec, names, state = self.torch, self.codec, self.names, self.state
+        if e2e:
+            frames = {f: tuple(p.to(self.dev, non_blocking=True) for p in self.host[f]) for f in names}
+        else:
+            frames = self.resident
+        t0 = time.perf_counter()
+        bts, rec = codec.encode_gop(frames, self.gop)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        dec = codec.decode_gop(bts, self.gop)
+        torch.cuda.synchronize()
+        state['enc_s'] = state.get('enc_s', 0.0) + (t1 - t0)
+        state['dec_s'] = state.get('dec_s', 0.0) + (time.perf_counter() - t1)
+        if e2e:
+            for f in names:
+                for d, s in zip(self.out_host[f], dec[f]):
+                    d.copy_(s, non_blocking=True)
+        state['bts'], state['rec'], state['dec'] = bts, rec, dec
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, e2e, profile, steps):
+        torch, L, codec = self.torch, self.L, self.codec
+        self.barrier()
+        l0 = L.aivc_launch_count()
+        if profile:
+            L.aivc_profile_enable(1)
+        # per-stage timing needs kernels one at a time: no second stream next to the timed stages
+        # (the library likewise drops its two-lane execution while profiling)
+        overlap = codec.mof.overlap_shortcut
+        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap and not profile
+        sampler = ClockSampler(self.local) if self.rank == 0 else None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            self.step(e2e)
+        b.record()
+        self.barrier()
+        ms = a.elapsed_time(b)
+        clocks = sampler.stop() if sampler else None
+        prof = None
+        if profile:
+            out = (C.c_double * 6)()
+            self._lib.check(L.aivc_profile_read(out))
+            ncls = len(self._lib.KERNEL_CLASSES)
+            cls = (C.c_double * (3 * ncls))()
+            self._lib.check(L.aivc_profile_read_classes(cls, ncls))
+            prof = list(out) + list(cls)
+            if self.args.stage_csv and self.rank == 0:
+                self._lib.check(L.aivc_profile_dump(self.args.stage_csv.encode()))
+            L.aivc_profile_enable(0)
+        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
+        launches = L.aivc_launch_count() - l0
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks, prof, launches
+
+    def check_closed_loop(self, what):
+        """decoder output == encoder reconstruction on the data of the last step"""
+        for f in self.names:
+            for x, y in zip(self.state['rec'][f], self.state['dec'][f]):
+                assert self.torch.equal(x, y), 'closed loop broken (%s leg, %s, %s)' % (what, self.precision, f)
+
+    def check_e2e_output(self):
+        """the planes that came back to pinned host memory in the e2e leg are the encoder's reconstruction"""
+        self.torch.cuda.synchronize()
+        for f in self.names:
+            for h_, d_ in zip(self.out_host[f], self.state['rec'][f]):
+                assert self.torch.equal(h_, d_.cpu()), 'e2e leg returned wrong planes (%s, %s)' % (self.precision, f)
+
+
+def roofline_of(prof, steps, ms_prof, precision, kernel_classes):
+    peak_tf, peak_bw, peak_src = peaks()
+    mma_per_flop = 3.0 if precision == 'bf16x3' else 1.0     # tensor-core work per algorithmic FLOP
+    peak_alg = peak_tf / mma_per_flop
+    tc_ms, tc_fl, tc_n, si_ms, si_fl, si_n = prof[:6]
+    ach_all = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    by_kernel, all_ms = {}, sum(prof[6 + 3 * k] for k in range(len(kernel_classes)))
+    for k, name in enumerate(kernel_classes):
+        k_ms, k_fl, k_n = prof[6 + 3 * k: 9 + 3 * k]
+        if k_n:
+            tf = k_fl / (k_ms * 1e-3) / 1e12
+            by_kernel[name] = {'launches_per_step': k_n / steps, 'avg_launch_us': 1e3 * k_ms / k_n, 'tflops': tf,
+                               'frac': tf / peak_alg, 'share_of_stage_time': k_ms / all_ms}
+    dom = max((n for n in by_kernel if by_kernel[n]['tflops'] > 0), key=lambda n: by_kernel[n]['share_of_stage_time'])
+    ach = by_kernel[dom]['tflops']
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')     # dram bytes per launch from the ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(precision, {}).get(dom)
+    return {
+        'bound': 'tensor', 'achieved': ach, 'peak': peak_alg, 'unit': 'TFLOP/s', 'frac': ach / peak_alg,
+        'traffic': traffic,
+        'peak_source': peak_src + ('; bf16x3 issues three bf16 MMAs (hi.Whi + lo.Whi + hi.Wlo) per algorithmic multiply-add, so the '
+                                   'peak for ALGORITHMIC FLOP/s is the measured bf16 rate / 3 (SURVEY.md 8d: "report against '
+                                   'the corresponding peak"); tensor-pipe rate = 3 x achieved = %.0f TFLOP/s of %.0f'
+                                   % (3 * ach, peak_tf) if precision == 'bf16x3' else ''),
+        'kernel': dom + ' (the kernel with the largest share of GPU time)',
+        'how': 'algorithmic FLOPs (SURVEY.md 8d) of this kernel\'s launches in K timed steps / sum of their CUDA-event '
+               'durations on the launching stream (second pass of the same K steps, an event pair around every '
+               'convolution stage); `traffic` = DRAM bytes of one representative launch (ncu --set full, profiles/)',
+        'launches_per_step': by_kernel[dom]['launches_per_step'],
+        'avg_launch_us': by_kernel[dom]['avg_launch_us'],
+        'share_of_stage_time': by_kernel[dom]['share_of_stage_time'],
+        'by_kernel': by_kernel,
+        'all_tensor_stages': {'tflops': ach_all, 'frac': ach_all / peak_alg, 'stages': int(tc_n)},
+        'tc_ms_per_step': tc_ms / steps, 'tc_share_of_step': tc_ms / ms_prof,
+        'profiled_ms_per_step': ms_prof / steps,
+        'simt_ms_per_step': si_ms / steps, 'simt_tflops': si_fl / max(si_ms, 1e-9) / 1e9,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from aivc_b200 import models, gop as G, _lib
-    from aivc_b200.codec import FrameCodec
-    from aivc_b200.plan import Config
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -186,153 +385,170 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    L = _lib.lib()
+    if args.sharding == 'frame':
+        return run_frame_sharded(args, dev, world, rank, local)
 
     net = models.build_standin(**MODEL)
     gop = G.generate_gop_struct(GOP_NAME)
     names = sorted(gop, key=lambda f: int(f.split('_')[1]))
-    codec = FrameCodec(net, H, W, dev, Config(precision=args.precision))
     clip = synth_gop(100 + rank, len(names))
     host = {f: tuple(torch.from_numpy(p.reshape(-1)).pin_memory() for p in clip[i]) for i, f in enumerate(names)}
     resident = {f: tuple(p.to(dev) for p in host[f]) for f in names}
-    out_host = {f: tuple(torch.empty_like(p) for p in host[f]) for f in names}
+    out_host = {f: tuple(torch.empty_like(p).pin_memory() for p in host[f]) for f in names}
     frame_bytes = sum(p.numel() for p in host[names[0]])
-    state = {}
+    common = (net, gop, names, host, resident, out_host, dev, world, rank, local, args)
 
-    def step(e2e):
-        if e2e:
-            frames = {f: tuple(p.to(dev, non_blocking=True) for p in host[f]) for f in names}
-        else:
-            frames = resident
-        t0 = time.perf_counter()
-        bts, rec = codec.encode_gop(frames, gop)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        dec = codec.decode_gop(bts, gop)
-        torch.cuda.synchronize()
-        state['enc_s'] = state.get('enc_s', 0.0) + (t1 - t0)
-        state['dec_s'] = state.get('dec_s', 0.0) + (time.perf_counter() - t1)
-        if e2e:
-            for f in names:
-                for d, s in zip(out_host[f], dec[f]):
-                    d.copy_(s, non_blocking=True)
-        state['bts'], state['rec'], state['dec'] = bts, rec, dec
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(e2e, profile):
-        barrier()
-        l0 = L.aivc_launch_count()
-        if profile:
-            L.aivc_profile_enable(1)
-        # per-stage timing needs kernels one at a time: no second stream next to the timed stages
-        # (the library likewise drops its two-lane execution while profiling)
-        overlap = codec.mof.overlap_shortcut
-        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap and not profile
-        sampler = ClockSampler(local) if rank == 0 else None
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            step(e2e)
-        b.record()
-        barrier()
-        ms = a.elapsed_time(b)
-        clocks = sampler.stop() if sampler else None
-        prof = None
-        if profile:
-            out = (C.c_double * 6)()
-            _lib.check(L.aivc_profile_read(out))
-            ncls = len(_lib.KERNEL_CLASSES)
-            cls = (C.c_double * (3 * ncls))()
-            _lib.check(L.aivc_profile_read_classes(cls, ncls))
-            prof = list(out) + list(cls)
-            if args.stage_csv and rank == 0:
-                _lib.check(L.aivc_profile_dump(args.stage_csv.encode()))
-            L.aivc_profile_enable(0)
-        codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
-        launches = L.aivc_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, clocks, prof, launches
-
+    arm = Arm(args.precision, *common)
     for _ in range(args.warmup):
-        step(False)
-    state['enc_s'] = state['dec_s'] = 0.0
-    ms, clocks, _, launches = timed(False, False)
-    enc_ms, dec_ms = 1e3 * state['enc_s'] / args.steps, 1e3 * state['dec_s'] / args.steps
+        arm.step(False)
+    arm.state['enc_s'] = arm.state['dec_s'] = 0.0
+    ms, clocks, _, launches = arm.timed(False, False, args.steps)
+    enc_ms, dec_ms = 1e3 * arm.state['enc_s'] / args.steps, 1e3 * arm.state['dec_s'] / args.steps
+    arm.check_closed_loop('resident')
     # roofline leg: the same K steps again with a CUDA-event pair around every convolution stage
-    # (the event records sit between kernels, which costs ~4% of step time, so the headline
+    # (the event records sit between kernels, which costs a few % of step time, so the headline
     # `value` above is taken without them)
-    ms_prof, _, prof, _ = timed(False, True)
-    # closed loop must hold on the benchmarked data (decoder == encoder reconstruction)
-    for f in names:
-        for x, y in zip(state['rec'][f], state['dec'][f]):
-            assert torch.equal(x, y), 'closed loop broken on ' + f
-    total_bytes = sum(len(b) for b in state['bts'].values())
-    step(True)
-    ms_e2e, _, _, _ = timed(True, False)
+    ms_prof, _, prof, _ = arm.timed(False, True, args.steps)
+    total_bytes = sum(len(b) for b in arm.state['bts'].values())
+    arm.step(True)
+    ms_e2e, _, _, _ = arm.timed(True, False, args.steps)
+    arm.check_closed_loop('e2e')
+    arm.check_e2e_output()
 
     frames_per_step = len(names) * world
     value = frames_per_step * args.steps / (ms / 1000.0)
     e2e = frames_per_step * args.steps / (ms_e2e / 1000.0)
     if rank == 0:
-        peak_tf, peak_bw, peak_src = peaks()
-        tc_ms, tc_fl, tc_n, si_ms, si_fl, si_n = prof[:6]
-        ach_all = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        # per kernel: algorithmic FLOPs of its launches / their CUDA-event durations
-        by_kernel, all_ms = {}, sum(prof[6 + 3 * k] for k in range(len(_lib.KERNEL_CLASSES)))
-        for k, name in enumerate(_lib.KERNEL_CLASSES):
-            k_ms, k_fl, k_n = prof[6 + 3 * k: 9 + 3 * k]
-            if k_n:
-                by_kernel[name] = {'launches_per_step': k_n / args.steps, 'avg_launch_us': 1e3 * k_ms / k_n,
-                                   'tflops': k_fl / (k_ms * 1e-3) / 1e12, 'share_of_stage_time': k_ms / all_ms}
-        dom = max((n for n in by_kernel if by_kernel[n]['tflops'] > 0), key=lambda n: by_kernel[n]['share_of_stage_time'])
-        ach = by_kernel[dom]['tflops']
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')     # dram bytes per launch from the ncu --set full captures
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split bf16 operands, fp32 accumulate)', 'fp32': 'f32'}[args.precision],
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split-bf16 operands on tcgen05, fp32 accumulate: fp32-grade)',
+                      'fp32': 'f32'}[args.precision],
+            'precision': args.precision,
             'data': 'synthetic', 'config': workload_config(world), 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': frame_bytes * len(names), 'd2h_bytes_per_step': frame_bytes * len(names),
+                    'output_checked': True,
                     'note': 'frames start in pinned host memory and decoded planes return to pinned host memory '
-                            'every step; the bitstream (bytes) is produced/consumed on the host in both modes'},
+                            'every step (compared with the encoder\'s reconstruction after the timed region); the '
+                            'bitstream (bytes) is produced/consumed on the host in both modes'},
             'gpu_launches': int(launches),
-            'roofline': {
-                'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
-                'traffic': traffic, 'peak_source': peak_src,
-                'kernel': dom + ' (the kernel with the largest share of GPU time)',
-                'how': 'algorithmic FLOPs of this kernel\'s launches in K timed steps / sum of their CUDA-event '
-                       'durations on the launching stream (second pass of the same K steps, an event pair '
-                       'around every convolution stage); `traffic` = DRAM bytes of one representative launch '
-                       '(ncu --set full, profiles/)',
-                'launches_per_step': by_kernel[dom]['launches_per_step'],
-                'avg_launch_us': by_kernel[dom]['avg_launch_us'],
-                'share_of_stage_time': by_kernel[dom]['share_of_stage_time'],
-                'by_kernel': by_kernel,
-                'all_tensor_stages': {'tflops': ach_all, 'frac': ach_all / peak_tf, 'stages': int(tc_n)},
-                'tc_ms_per_step': tc_ms / args.steps, 'tc_share_of_step': tc_ms / ms_prof,
-                'profiled_ms_per_step': ms_prof / args.steps,
-                'simt_ms_per_step': si_ms / args.steps, 'simt_tflops': si_fl / max(si_ms, 1e-9) / 1e9,
-            },
+            'roofline': roofline_of(prof, args.steps, ms_prof, args.precision, _lib.KERNEL_CLASSES),
             'bitstream_bytes_per_gop': total_bytes, 'encode_ms_per_gop': enc_ms, 'decode_ms_per_gop': dec_ms,
             'encode_fps': 33e3 / enc_ms, 'decode_fps': 33e3 / dec_ms,
             'encode_decode_closed_loop': True,
         }
+        if world == 1 and not args.quick:
+            # parity of THIS engine against the CPU oracle's fixture at the benchmark's resolution (1080p I, P, B;
+            # tests/parity_cfg.py, fixture minted by oracle/gen_golden_configs.py)
+            from tests import parity_cfg
+            keys = ('y_symbols', 'y_mismatches', 'y_index_mismatch_rate', 'y_max_abs_diff', 'z_symbols', 'z_mismatches',
+                    'bytes', 'oracle_bytes', 'bytes_delta', 'frames_bytes_identical', 'max_level_diff_subsampled',
+                    'max_abs_psnr_delta_db', 'closed_loop_exact')
+            r = parity_cfg.measure('ra1080', args.precision, dev)
+            line['parity'] = dict({k: r[k] for k in keys}, psnr_delta_db=r['max_abs_psnr_delta_db'],
+                                  vs='CPU oracle fixture tests/golden/cfg_ra1080.npz (1080p I, P, B; stand-in with live hyperprior)')
+            # the other tensor-core precision next to the headline one, same workload, same run
+            other = 'bf16' if args.precision != 'bf16' else 'bf16x3'
+            del arm
+            torch.cuda.empty_cache()
+            alt = Arm(other, *common)
+            alt.step(False)
+            alt.step(False)
+            ms_a, _, _, _ = alt.timed(False, False, args.steps)
+            alt.check_closed_loop('resident')
+            alt.step(True)
+            ms_ae, _, _, _ = alt.timed(True, False, args.steps)
+            alt.check_e2e_output()
+            ms_ap, _, prof_a, _ = alt.timed(False, True, args.steps)
+            rf = roofline_of(prof_a, args.steps, ms_ap, other, _lib.KERNEL_CLASSES)
+            ra = parity_cfg.measure('ra1080', other, dev)
+            line['other_precision'] = {
+                'precision': other, 'value': frames_per_step * args.steps / (ms_a / 1000.0),
+                'e2e': frames_per_step * args.steps / (ms_ae / 1000.0), 'unit': 'frames/s',
+                'roofline': {k: rf[k] for k in ('kernel', 'achieved', 'peak', 'frac', 'all_tensor_stages')},
+                'parity': {k: ra[k] for k in keys},
+                'note': 'bf16: plain bf16 operands -- the fastest mode, ~1 % of the latent indices differ from fp32 '
+                        'arithmetic; bf16x3: the fp32-faithful default'}
+            del alt
+            torch.cuda.empty_cache()
+            line['gpu_library_baseline'] = dict(gpu_library_baseline(dev), note='eager PyTorch (cuDNN) on this GPU: g_a / g_s of '
+                                                'the CodecNet stand-in at 1080p, ms per call; the fused plans of this repo take '
+                                                'the times in roofline.by_kernel')
         if world == 1 and not args.no_cpu_baseline:
-            fps, threads, sample = cpu_reference_sample(15.0)
+            fps, threads, sample, _ = cpu_reference_sample(25.0)
             line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                     'sample': sample}
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_frame_sharded(args, dev, world, rank, local):
+    """--sharding frame: ONE GOP per step, its frames dealt over the ranks by dependency level, every new 8-bit
+    reconstruction broadcast over NCCL before the next level (BASELINE.json configs[3]).  Latency
+    mode: value = frames of the GOP / time of the slowest rank."""
+    import torch
+    import torch.distributed as dist
+    from aivc_b200 import models, gop as G, sharding, _lib
+    from aivc_b200.codec import FrameCodec
+    from aivc_b200.plan import Config
+    net = models.build_standin(**MODEL)
+    gop = G.generate_gop_struct(GOP_NAME)
+    names = sorted(gop, key=lambda f: int(f.split('_')[1]))
+    codec = FrameCodec(net, H, W, dev, Config(precision=args.precision))
+    clip = synth_gop(100, len(names))                    # every rank holds the whole GOP's source frames
+    frames = {f: tuple(torch.from_numpy(p.reshape(-1)).to(dev) for p in clip[i]) for i, f in enumerate(names)}
+    L = _lib.lib()
+    stats = {}
+
+    def step():
+        bts, rec = sharding.encode_gop_frame_parallel(codec, frames, gop, rank, world, stats=stats)
+        dec = sharding.decode_gop_frame_parallel(codec, bts, gop, rank, world, stats=stats)
+        return bts, rec, dec
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    stats.clear()
+    l0 = L.aivc_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        bts, rec, dec = step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for f in names:
+        for x, y in zip(rec[f], dec[f]):
+            assert torch.equal(x, y), 'closed loop broken on ' + f
+    import hashlib
+    md5 = hashlib.md5(b''.join(bts[f] for f in names)).hexdigest()
+    if rank == 0:
+        value = len(names) * args.steps / (ms / 1000.0)
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': args.precision, 'precision': args.precision, 'data': 'synthetic',
+            'config': workload_config(world, 'frame'), 'clocks': clocks,
+            'gpu_launches': int(L.aivc_launch_count() - l0),
+            'gop_latency_ms': ms / args.steps,
+            'broadcast_ms_per_step': 1e3 * stats.get('bcast_s', 0.0) / args.steps,
+            'broadcasts_per_step': stats.get('bcasts', 0) / args.steps,
+            'bitstream_md5': md5, 'bitstream_bytes_per_gop': sum(len(bts[f]) for f in names),
+            'encode_decode_closed_loop': True,
+            'note': 'one GOP per step over all ranks (strong scaling, latency mode); the bitstream md5 is identical for every N'}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -343,8 +559,12 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16', 'fp32'],
+                    help='bf16x3 (default): fp32-faithful split-bf16 tensor-core mode; bf16: fastest; fp32: exact SIMT engine')
+    ap.add_argument('--sharding', default='gop', choices=['gop', 'frame'],
+                    help='gop: one GOP per rank (throughput, no collective); frame: one GOP over all ranks (latency, NCCL broadcasts)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='skip the parity / other-precision / library-baseline legs')
     ap.add_argument('--stage-csv', default='', help='dump per-stage CUDA-event timings of the timed region')
     args = ap.parse_args()
     import __graft_entry__ as g

@@ -184,10 +184,12 @@ int aivc_yuv420_pack16(const void *y0, const void *u0, const void *v0, const voi
  * (decode.py:729-739, 524-536; optical_flow.py:14-55).  mof: 6 channels (alpha, beta,
  * v_prev xy, v_next xy).  frame_is_p: beta := 1, v_next := 0.
  * pred = alpha * x_warp (3 ch, same units as prev/next), skip = (1 - alpha) * x_warp (3 ch,
- * always [0,1] units; levels != 0 says prev/next hold 8-bit level units). */
+ * always [0,1] units; levels != 0 says prev/next hold 8-bit level units).
+ * aux: NULL, or fp32 [5][h][w] = alpha, beta, x_warp (3 planes, [0,1] units): the tensors the (missing)
+ * encoder returns as net_out['alpha' | 'beta' | 'warping'] for logging (loss_function.py:179-204). */
 int aivc_warp_blend(const aivc_fmap *mof, const aivc_fmap *prev, const aivc_fmap *next,
                     int frame_is_p, int levels, const aivc_fmap *pred, const aivc_fmap *skip,
-                    void *stream);
+                    float *aux, void *stream);
 /* stand-alone motion compensation for the drop-in MotionCompensation module:
  * all tensors NCHW fp32, beta [3][h][w], flows [2][h][w]. */
 int aivc_warp_blend_nchw(const float *prev, const float *next, const float *v_prev,
@@ -213,10 +215,19 @@ int aivc_mu_sigma_nchw(const float *hs, float *mu, float *sigma, int c, int hw, 
  *   bounds : uint32 NCHW, c_low | c_high<<16 = 16-bit CDF bounds of q under Laplace(0, sigma/sqrt 2)
  *   nz     : int32 [C], set to 1 where the channel has a non-zero symbol (zero it first)
  *   yhat   : C channels = (q + mu) * dec_gain   (input of g_s; decode.py:867-885)
+ *   rate   : NULL, or fp32 [C][h][w]: the encoder-side rate ESTIMATE of every symbol in bits,
+ *            -log2 clamp(cdf(q + 1/2) - cdf(q - 1/2), 2^-16, 1) for the Laplace of scale sigma/sqrt(2)
+ *            (ParametricPdf.forward with zero_mu, pdf_estimator.py:27-70; EntropyCoder.forward,
+ *            entropy_coder.py:25-30) -- what the reference logs as `*_rate_y` (loss_function.py:158,186)
  */
 int aivc_quantize_latent(const aivc_fmap *y, const aivc_fmap *hs, const float *dec_gain,
                          int16_t *q, uint32_t *bounds, int32_t *nz, const aivc_fmap *yhat,
-                         void *stream);
+                         float *rate, void *stream);
+/* ParametricPdf.forward (pdf_estimator.py:27-70), one mixture component, contiguous fp32 tensors of n elements:
+ * out (+)= cdf(y + 1/2) - cdf(y - 1/2) for Laplace(mu, sigma/sqrt(2)) (family 0) or Normal(mu, sigma) (family 1);
+ * mu == NULL: zero mean (zero_mu / the '*_mu' families); accumulate != 0 adds to `out` (mixtures). */
+int aivc_pdf_prob(const float *y, const float *mu, const float *sigma, int family, int accumulate, float *out,
+                  size_t n, void *stream);
 /* Decoder side: scale b = sigma/sqrt(2) per symbol, fp32 NCHW, for the host range decoder. */
 int aivc_laplace_scale(const aivc_fmap *hs, int c, float *b, void *stream);
 /* Same, plus win[8] per symbol (uint16, NCHW symbol order, 16-byte aligned): the integer CDF entries

@@ -116,9 +116,15 @@ def test_mu_sigma_and_cdf_bounds_exact(golden_dir, dev):
     bounds = torch.empty(c * h * w, dtype=torch.int32, device=dev)
     nz = torch.zeros(c, dtype=torch.int32, device=dev)
     fy, fh, fo = ybuf.view(), hsbuf.view(), yhat.view()
+    rate = torch.empty(c * h * w, dtype=torch.float32, device=dev)
     _lib.check(L.aivc_quantize_latent(C.byref(fy), C.byref(fh), gain.data_ptr(), q.data_ptr(),
-                                      bounds.data_ptr(), nz.data_ptr(), C.byref(fo), _lib.stream_ptr()))
+                                      bounds.data_ptr(), nz.data_ptr(), C.byref(fo), rate.data_ptr(),
+                                      _lib.stream_ptr()))
     qn = q.cpu().numpy().reshape(c, h, w)
+    # rate estimate of every symbol (pdf_estimator.py:27-70 + entropy_coder.py:25-30) against torch's evaluation
+    from oracle import nn_ref as R
+    ref_rate = R.laplace_rate_bits(torch.from_numpy(qn.astype(np.float32))[None], torch.from_numpy(fx['sigma'])).numpy()
+    np.testing.assert_allclose(rate.cpu().numpy().reshape(1, c, h, w), ref_rate, rtol=2e-5, atol=2e-5)
     ref_q = np.clip(np.rint(y - fx['mu'][0]), -256, 255).astype(np.int16)
     assert np.array_equal(qn, ref_q)
     assert list(nz.cpu().numpy()) == [1, 1, 0, 1, 1, 0, 1, 1]
@@ -210,3 +216,35 @@ def test_closed_loop_odd_and_reference_sizes(size, dev):
         assert len(bts[f]) > 16
         for a, b in zip(rec[f], dec[f]):
             assert torch.equal(a, b)
+
+
+def test_entropy_model_classes_vs_reference_golden(golden_dir, dev):
+    """ParametricPdf / EntropyCoder / PdfParamParameterizer (mixture modes) / BallePdfEstim.forward mirrors against
+    fixtures the REFERENCE's classes produced (oracle/gen_golden_pdf.py): pdf_estimator.py:17-70, 172-202,
+    entropy_coder.py:18-30, misc_layers.py:172-269.  Tolerance: torch's expm1 / erf against ours, 2e-6 absolute on
+    probabilities (values <= 1)."""
+    import aivc_b200.layers as M
+    fx = np.load(os.path.join(golden_dir, 'pdf_classes.npz'))
+    C_ = 6
+    for mode in ('laplace', 'laplace_two', 'normal_three_gamma'):
+        x = torch.from_numpy(fx['pp_%s_x' % mode]).to(dev)
+        prm = M.PdfParamParameterizer(mode, C_)(x)
+        K = 1 + ('two' in mode) + 2 * ('three' in mode)
+        assert len(prm) == K
+        for k, d in enumerate(prm):
+            assert np.array_equal(d['mu'].cpu().numpy(), fx['pp_%s_%d_mu' % (mode, k)])
+            np.testing.assert_allclose(d['sigma'].cpu().numpy(), fx['pp_%s_%d_sigma' % (mode, k)], rtol=3e-7)
+            np.testing.assert_allclose(d['gamma'].cpu().numpy(), fx['pp_%s_%d_gamma' % (mode, k)], rtol=3e-7)
+            np.testing.assert_allclose(d['weight'].cpu().numpy(), fx['pp_%s_%d_weight' % (mode, k)], rtol=1e-6, atol=1e-7)
+        y = torch.from_numpy(fx['pdf_%s_y' % mode]).to(dev)
+        fam = 'normal' if 'normal' in mode else 'laplace'
+        for zero_mu in (False, True):
+            p = M.ParametricPdf(fam)(y, prm, zero_mu=zero_mu)
+            np.testing.assert_allclose(p.cpu().numpy(), fx['pdf_%s_zero%d_p' % (mode, zero_mu)], rtol=0, atol=2e-6)
+            rate = M.EntropyCoder()(torch.from_numpy(fx['pdf_%s_zero%d_p' % (mode, zero_mu)]).to(dev), y)
+            np.testing.assert_allclose(rate.cpu().numpy(), fx['pdf_%s_zero%d_rate' % (mode, zero_mu)], rtol=1e-6, atol=1e-6)
+    bz = M.BallePdfEstim(C_, pdf_family='')
+    bz.load_state_dict({k[9:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith('balle_sd:')})
+    with torch.no_grad():
+        p = bz(torch.from_numpy(fx['balle_z']))
+    np.testing.assert_allclose(p.numpy(), fx['balle_p'], rtol=1e-6, atol=1e-7)

@@ -43,6 +43,38 @@ def test_gop_forward_contract_and_video_roundtrip(golden_dir, dev, tmp_path):
         for k in 'yuv':
             got = (out[f]['x_hat'][k].cpu().numpy() * 255).round().astype(np.uint8).reshape(-1)
             assert np.array_equal(got, fx['spec_rec_%s_%s' % (f, k)].reshape(-1))     # fp32 engine == oracle
+    # the logging tensors are the real ones: rate estimates, alpha, beta, warping against the
+    # oracle's evaluation of the same frames (fp32 engine: same symbols, so the only difference is fp32 rounding)
+    from oracle import codec_ref as O, nn_ref as R
+    tables = O.Tables(net)
+    yuv = {f: {k: raw[f][k].cpu() for k in 'yuv'} for f in raw}
+    orec = {}
+    for f in sorted(gop, key=lambda f: gop[f]['coding_order']):
+        t = gop[f]['type']
+        prev = orec[gop[f]['prev_ref']] if t != 0 else O.zero_yuv(h, w)
+        nxt = orec[gop[f]['next_ref']] if t == 2 else O.zero_yuv(h, w)
+        _, orec[f], aux = O.encode_frame(net, tables, yuv[f], prev, nxt, t)
+        o = out[f]
+        for net_name, key, cn in (('mof', 'mode', net.mode_net.mode_net), ('codec', 'codec', net.codec_net.codec_net)):
+            if net_name not in aux:
+                assert float(o[key + '_rate_y'].sum()) == 0.0 and float(o[key + '_rate_z'].sum()) == 0.0
+                continue
+            ref_y = R.laplace_rate_bits(aux[net_name]['q'], aux[net_name]['sigma'])
+            np.testing.assert_allclose(o[key + '_rate_y'].cpu().numpy(), ref_y.numpy(), rtol=2e-5, atol=2e-5)
+            with torch.no_grad():
+                ref_z = -torch.log2(torch.clamp(cn.pdf_z(aux[net_name]['z_hat']), 2.0 ** -16, 1.0))
+            np.testing.assert_allclose(o[key + '_rate_z'].cpu().numpy(), ref_z.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(o['alpha'].cpu().numpy(), aux['alpha'].expand(1, 3, h, w).numpy(), atol=2e-5)
+        np.testing.assert_allclose(o['warping'].cpu().numpy(), aux['x_warp'].numpy(), atol=2e-5)
+        assert o['beta'].shape == (1, 3, h, w) and float(o['beta'].min()) >= 0.0 and float(o['beta'].max()) <= 1.0
+        if t == 1:
+            assert float(o['beta'].min()) == 1.0                       # P frames: beta = 1 (decode.py:736-739)
+        # estimated rate vs real coded size: the range coder is within a few % + a few bytes of the estimate
+        est = float(o['codec_rate_y'].sum() + o['codec_rate_z'].sum())
+        real = o['coded_bits']['codec_y'] + o['coded_bits']['codec_z']
+        assert abs(real - est) <= 0.1 * est + 256, (est, real)
+    m = adapter.compute_metrics_one_gop(out, raw)
+    assert set(m) == set(gop) | {'GOP'} and m['GOP']['total_rate_bpp'] > 0 and 0 < m['frame_0']['ms_ssim'] <= 1
     gbytes = open(d + '0g', 'rb').read()
     name, rate, frames = container.unpack_gop(gbytes)
     assert name == '1_GOP_2' and [bytes(b) for b in frames] == [fx['spec_bytes_frame_%d' % i].tobytes() for i in range(3)]
