@@ -179,19 +179,27 @@ int smem_attr_once(const void *kernel, int bytes) {
 
 extern "C" {
 
-struct Lanes { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static Lanes g_lanes[16];
+// Two-lane execution of a plan: the side stream + fork / join events belong to the CALLER'S stream, so that
+// plans enqueued on different streams (two frames in flight, the encoder's shortcut transform next to the analysis
+// chain) never funnel their side stages through one shared stream.  Small table per process, mutex-protected.
+struct Lanes { int dev = -1; cudaStream_t main = nullptr, side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static Lanes g_lanes[64];
+static int g_nlanes = 0;
+static std::mutex g_lanes_mu;
 
-static int lanes_for_current_device(Lanes **out) {
+static int lanes_for_stream(cudaStream_t main_s, Lanes **out) {
     int dev = 0;
     AIVC_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) AIVC_FAIL("device index %d out of range", dev);
-    Lanes &l = g_lanes[dev];
-    if (!l.side) {
-        AIVC_CHECK_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
-        AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
-        AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
-    }
+    std::lock_guard<std::mutex> lock(g_lanes_mu);
+    for (int i = 0; i < g_nlanes; ++i)
+        if (g_lanes[i].dev == dev && g_lanes[i].main == main_s) { *out = &g_lanes[i]; return 0; }
+    if (g_nlanes == 64) AIVC_FAIL("more than 64 (device, stream) pairs run two-lane plans");
+    Lanes &l = g_lanes[g_nlanes];
+    l.dev = dev; l.main = main_s;
+    AIVC_CHECK_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+    AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    ++g_nlanes;
     *out = &l;
     return 0;
 }
@@ -202,7 +210,7 @@ int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
     bool side_dirty = false;
     for (int i = 0; i < n; ++i) {
         const int flags = g_prof_on ? 0 : ops[i].flags;   // per-stage timing needs kernels one at a time
-        if (flags && !l && lanes_for_current_device(&l)) return 1;
+        if (flags && !l && lanes_for_stream(main_s, &l)) return 1;
         if (flags & AIVC_OP_FORK) {
             AIVC_CHECK_CUDA(cudaEventRecord(l->fork, main_s));
             AIVC_CHECK_CUDA(cudaStreamWaitEvent(l->side, l->fork, 0));

@@ -42,10 +42,14 @@ class Config:
     hyper: str = 'auto'            # precision of h_a / h_s: 'fp32' (exact engine), 'bf16', or
                                    # 'auto' = same as `precision`
     two_lanes: bool = True         # independent branches of attention blocks on two CUDA streams
-    s2d_first: bool = True         # bf16: 5x5 stride-2 pixel-domain first layer as space-to-depth + 3x3 conv
+    s2d_first: bool = True         # tensor-core engines: 5x5 stride-2 pixel-domain first layer as space-to-depth + 3x3 conv
+    frames_in_flight: int = 1      # GOP coding: independent frames of a dependency level on this many streams
+                                   # (codec.py::_lanes).  Measured on B200 (tools/lanes_ab.py): 2 lanes give +1 % (bf16x3)
+                                   # / +2 % (bf16) for twice the buffers -- the device is already 95 % busy and
+                                   # power-capped with one frame in flight -- so one lane is the default
 
     def key(self):
-        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first)
+        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first, self.frames_in_flight)
 
     @property
     def tc(self):
@@ -59,7 +63,7 @@ class Config:
     def hyper_cfg(self):
         h = self.precision if self.hyper == 'auto' else self.hyper
         return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h, two_lanes=self.two_lanes,
-                      s2d_first=self.s2d_first)
+                      s2d_first=self.s2d_first, frames_in_flight=self.frames_in_flight)
 
 
 DEFAULT = Config()

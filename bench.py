@@ -289,6 +289,7 @@ class Arm:
         # (the library likewise drops its two-lane execution while profiling)
         overlap = codec.mof.overlap_shortcut
         codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap and not profile
+        codec.lanes_enabled = not profile             # (likewise: one frame in flight while stages are timed)
         sampler = ClockSampler(self.local) if self.rank == 0 else None
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -310,6 +311,7 @@ class Arm:
                 self._lib.check(L.aivc_profile_dump(self.args.stage_csv.encode()))
             L.aivc_profile_enable(0)
         codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
+        codec.lanes_enabled = True
         launches = L.aivc_launch_count() - l0
         if self.world > 1:
             import torch.distributed as dist

@@ -59,9 +59,7 @@ def measure(case, precision, dev, codec=None):
             key = '%s_%s_q' % (f, net_name)
             if key not in fx.files:
                 continue
-            sl = eng.slot(i)
-            q = sl.q.numpy().astype(np.int32).reshape(fx[key].shape)
-            z = sl.z.numpy().astype(np.int32).reshape(fx['%s_%s_z' % (f, net_name)].shape)
+            q, z = (a.astype(np.int32) for a in codec.decoded_symbols(f, net_name))
             dq = q - fx[key].astype(np.int32)
             dz = z - fx['%s_%s_z' % (f, net_name)].astype(np.int32)
             fr[net_name] = {'y_mismatches': int((dq != 0).sum()), 'z_mismatches': int((dz != 0).sum())}

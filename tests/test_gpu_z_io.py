@@ -173,7 +173,8 @@ def test_multi_gop_decode_with_lagging_gpu(precision, dev):
     video = container.pack_video((h, w), dy, dz, packed, 0, 3 * len(gops) - 1)
     # hold the GPU back in front of every synthesis pass: reconstruction of GOP g is still queued when the host
     # starts on GOP g + 1
-    for eng in (codec.mof, codec.codec):
+    engines = [e for c in codec._lanes() for e in (c.mof, c.codec)]         # (every lane of frames in flight)
+    for eng in engines:
         orig = eng.synth_launch
         def slow(*a, _orig=orig, **k):
             torch.cuda._sleep(20_000_000)               # ~10 ms
@@ -187,7 +188,7 @@ def test_multi_gop_decode_with_lagging_gpu(precision, dev):
                     for a, b in zip(rec[f], dec[g][f]):
                         assert torch.equal(a, b), (g, f)
     finally:
-        for eng in (codec.mof, codec.codec):
+        for eng in engines:
             del eng.synth_launch
 
 
@@ -223,3 +224,33 @@ def test_encoder_is_run_to_run_deterministic(precision, dev):
     for f in rec0:
         for p, q, r in zip(rec0[f], rec[f], dec[f]):
             assert torch.equal(p, q) and torch.equal(p, r), f
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_two_frames_in_flight_same_bitstream(precision, dev):
+    """Config.frames_in_flight = 2 deals the frames of a dependency level to two streams (two sets of plans and
+    buffers, events on the reconstructed planes).  Every frame is still coded by the same kernels in the same order:
+    bytes and planes are identical to the one-lane codec's, and the two-lane decoder reproduces them."""
+    from aivc_b200 import models, gop as G
+    from aivc_b200.codec import FrameCodec
+    from aivc_b200.plan import Config
+    h, w = 80, 112
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    gop = G.generate_gop_struct('1_GOP_8')               # levels of 1, 1, 1, 2, 4 frames
+    rng = np.random.default_rng(17)
+    from aivc_b200.codec import planes_to_device
+    frames = {f: planes_to_device([rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8),
+                                   rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)], dev) for f in gop}
+    one = FrameCodec(net, h, w, dev, Config(precision=precision, frames_in_flight=1))
+    two = FrameCodec(net, h, w, dev, Config(precision=precision, frames_in_flight=2))
+    b1, r1 = one.encode_gop(frames, gop)
+    for rep in range(3):
+        if rep == 1:
+            torch.cuda._sleep(100_000_000)               # vary the skew between the lanes
+        b2, r2 = two.encode_gop(frames, gop)
+        d2 = two.decode_gop(b2, gop)
+        assert b2 == b1
+        for f in gop:
+            for x, y, z in zip(r1[f], r2[f], d2[f]):
+                assert torch.equal(x, y) and torch.equal(x, z), (rep, f)
+    assert len(two._lanes()) == 2 and len(one._lanes()) == 1
