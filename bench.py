@@ -27,6 +27,22 @@ H, W = 1080, 1920
 GOP_NAME = '1_GOP_32'
 MODEL = dict(seed=1234, C=128, Cy=64, Cz=64, Csc=64)
 METRIC = '1080p frames/sec encode+decode'
+# frames of each type (I, P, B) in one GOP, and the 3-frame GOP the CPU arm samples (one frame of every type present)
+TYPE_COUNTS, SAMPLE_GOP = {0: 1, 1: 1, 2: 31}, '1_GOP_2'
+WORKLOAD = 'ra1080'
+
+
+def set_workload(name, seed=None):
+    """BASELINE.json configs: 'ra1080' = configs[2] (the headline; configs[3] is its --sharding frame form, configs[4]
+    its --model-seed sweep), 'ldp720' = configs[1] (low-delay P, 1280x720, GOP 8: I + 8 P, stand-in seed 4)."""
+    global H, W, GOP_NAME, MODEL, METRIC, TYPE_COUNTS, SAMPLE_GOP, WORKLOAD
+    WORKLOAD = name
+    if name == 'ldp720':
+        H, W, GOP_NAME, METRIC = 720, 1280, 'LDP_8', '720p frames/sec encode+decode'
+        MODEL = dict(MODEL, seed=4)
+        TYPE_COUNTS, SAMPLE_GOP = {0: 1, 1: 8, 2: 0}, 'LDP_2'
+    if seed is not None:
+        MODEL = dict(MODEL, seed=seed)
 
 
 def synth_gop(seed, n_frames, h=H, w=W):
@@ -120,8 +136,9 @@ def cpu_reference_sample(budget_s, threads=None):
     torch.set_num_threads(threads)
     net = models.build_standin(**MODEL)
     tables = O.Tables(net)
-    gop = G.generate_gop_struct('1_GOP_2')
+    gop = G.generate_gop_struct(SAMPLE_GOP)
     order = sorted(gop, key=lambda f: gop[f]['coding_order'])
+    n_of = {t: sum(1 for f in gop if gop[f]['type'] == t) for t in (0, 1, 2)}
 
     def run(rows):
         clip = synth_gop(0, 3, rows, W)
@@ -151,11 +168,15 @@ def cpu_reference_sample(budget_s, threads=None):
     per_row = sum(tp.values()) / probe_rows
     rows = int(min(H, max(32, budget_s / max(per_row, 1e-4))) // 16 * 16)
     t = run(rows)
-    gop_s = (t[0] + t[1] + 31.0 * t[2]) * (H / rows)
-    fps = 33.0 / gop_s
-    return fps, threads, ('I, P and B frame (1_GOP_2) encode+decode of a %dx%d crop of the 1080p clip: %.2f / %.2f / %.2f s; '
-                          'GOP of 33 frames = t_I + t_P + 31 t_B = %.0f s after scaling by area (x %.2f)'
-                          % (W, rows, t[0], t[1], t[2], gop_s, H / rows)), gop_s
+    per = {k: t[k] / max(n_of[k], 1) for k in t}                 # seconds per frame of each type
+    n_frames = sum(TYPE_COUNTS.values())
+    gop_s = sum(TYPE_COUNTS[k] * per[k] for k in per) * (H / rows)
+    fps = n_frames / gop_s
+    return fps, threads, ('one GOP %s (frame types I/P/B: %d/%d/%d) encode+decode of a %dx%d crop of the %dx%d clip: '
+                          '%.2f / %.2f / %.2f s per I / P / B frame; GOP %s of %d frames = %d t_I + %d t_P + %d t_B = %.0f s '
+                          'after scaling by area (x %.2f)'
+                          % (SAMPLE_GOP, n_of[0], n_of[1], n_of[2], W, rows, W, H, per[0], per[1], per[2], GOP_NAME, n_frames,
+                             TYPE_COUNTS[0], TYPE_COUNTS[1], TYPE_COUNTS[2], gop_s, H / rows)), gop_s
 
 
 def run_reference(args):
@@ -187,9 +208,11 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, sharding='gop'):
-    return {'workload': 'Random Access %s (33 frames/GOP), synthetic 1920x1080 YUV420, stand-in AIVC model '
-                        '(MOFNet+CodecNet, C=128, Cy=Cz=64, seed 1234); 1 GOP per GPU per step' % GOP_NAME,
-            'frames_per_step_per_gpu': 33, 'gop': GOP_NAME, 'resolution': '1920x1080',
+    n_frames = sum(TYPE_COUNTS.values())
+    return {'workload': '%s %s (%d frames/GOP), synthetic %dx%d YUV420, stand-in AIVC model '
+                        '(MOFNet+CodecNet, C=128, Cy=Cz=64, seed %d); 1 GOP per GPU per step'
+                        % ('Low-delay P' if WORKLOAD == 'ldp720' else 'Random Access', GOP_NAME, n_frames, W, H, MODEL['seed']),
+            'frames_per_step_per_gpu': n_frames, 'gop': GOP_NAME, 'resolution': '%dx%d' % (W, H),
             'sharding': 'one GOP per rank, no data-path collective' if sharding == 'gop' else
                         'frames of one GOP dealt over the ranks by dependency level, NCCL broadcast of every new 8-bit reconstruction',
             'l2': 'working set per step (activations > 2 GB, 102 MB of frames) exceeds the 126 MB L2'}
@@ -227,7 +250,9 @@ def gpu_library_baseline(dev):
         return a.elapsed_time(b) / reps
 
     out = {}
-    cases = {'g_a': (net.g_a, (1, 6, H, W)), 'g_s': (net.g_s, (1, net.nb_ft_y + net.out_c_shortcut_y, 68, 120))}
+    from aivc_b200.codec import latent_dims
+    (hy, wy), _ = latent_dims(H, W)
+    cases = {'g_a': (net.g_a, (1, 6, H, W)), 'g_s': (net.g_s, (1, net.nb_ft_y + net.out_c_shortcut_y, hy, wy))}
     with torch.no_grad():
         for name, (mod, shape) in cases.items():
             for label, dtype in (('fp32_tf32', torch.float32), ('bf16', torch.bfloat16)):
@@ -438,7 +463,7 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'roofline': roofline_of(prof, args.steps, ms_prof, args.precision, _lib.KERNEL_CLASSES),
             'bitstream_bytes_per_gop': total_bytes, 'encode_ms_per_gop': enc_ms, 'decode_ms_per_gop': dec_ms,
-            'encode_fps': 33e3 / enc_ms, 'decode_fps': 33e3 / dec_ms,
+            'encode_fps': 1e3 * len(names) / enc_ms, 'decode_fps': 1e3 * len(names) / dec_ms,
             'encode_decode_closed_loop': True,
         }
         if world == 1 and not args.quick:
@@ -448,9 +473,11 @@ def run_ours(args):
             keys = ('y_symbols', 'y_mismatches', 'y_index_mismatch_rate', 'y_max_abs_diff', 'z_symbols', 'z_mismatches',
                     'bytes', 'oracle_bytes', 'bytes_delta', 'frames_bytes_identical', 'max_level_diff_subsampled',
                     'max_abs_psnr_delta_db', 'closed_loop_exact')
-            r = parity_cfg.measure('ra1080', args.precision, dev)
+            case = 'ldp720' if WORKLOAD == 'ldp720' else 'ra1080'
+            r = parity_cfg.measure(case, args.precision, dev)
             line['parity'] = dict({k: r[k] for k in keys}, psnr_delta_db=r['max_abs_psnr_delta_db'],
-                                  vs='CPU oracle fixture tests/golden/cfg_ra1080.npz (1080p I, P, B; stand-in with live hyperprior)')
+                                  vs='CPU oracle fixture tests/golden/cfg_%s.npz (%s; stand-in with live hyperprior)'
+                                  % (case, '720p I, P, P' if case == 'ldp720' else '1080p I, P, B'))
             # the other tensor-core precision next to the headline one, same workload, same run
             other = 'bf16' if args.precision != 'bf16' else 'bf16x3'
             del arm
@@ -465,7 +492,7 @@ def run_ours(args):
             alt.check_e2e_output()
             ms_ap, _, prof_a, _ = alt.timed(False, True, args.steps)
             rf = roofline_of(prof_a, args.steps, ms_ap, other, _lib.KERNEL_CLASSES)
-            ra = parity_cfg.measure('ra1080', other, dev)
+            ra = parity_cfg.measure(case, other, dev)
             line['other_precision'] = {
                 'precision': other, 'value': frames_per_step * args.steps / (ms_a / 1000.0),
                 'e2e': frames_per_step * args.steps / (ms_ae / 1000.0), 'unit': 'frames/s',
@@ -568,7 +595,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick', action='store_true', help='skip the parity / other-precision / library-baseline legs')
     ap.add_argument('--stage-csv', default='', help='dump per-stage CUDA-event timings of the timed region')
+    ap.add_argument('--workload', default='ra1080', choices=['ra1080', 'ldp720'],
+                    help='ra1080: BASELINE configs[2] (default, the headline); ldp720: configs[1] (1280x720 low-delay P, GOP 8)')
+    ap.add_argument('--model-seed', type=int, default=None,
+                    help='stand-in weights seed (configs[4]: seeds 1..7 stand for the models ms_ssim-1..7)')
     args = ap.parse_args()
+    set_workload(args.workload, args.model_seed)
     import __graft_entry__ as g
     if int(os.environ.get('LOCAL_RANK', '0')) == 0:
         if not os.path.exists(os.path.join(ROOT, 'aivc_b200', 'libaivc_b200.so')):

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import aivc_b200.layers as M
 from aivc_b200.plan import Plan, Config
-from aivc_b200._lib import BF16
+from aivc_b200._lib import BF16, BF16X2
 
 class _GdnRes(torch.nn.Module):
     """x + igdn(conv3(x)): the residual flavour of the fused conv + GDN stage (lowered like a ChengResBlock tail)."""
@@ -51,6 +51,7 @@ def main():
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--reps', type=int, default=20, help='back-to-back runs per timing sample (L2-warm, as inside a transform)')
     ap.add_argument('--flush', action='store_true', help='flush L2 before every sample (use with --reps 1)')
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'bf16'])
     ap.add_argument('--f32-out', action='store_true', help='fp32 un-bordered output (default: bf16 + 1-pixel border, as inside a transform)')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -58,7 +59,8 @@ def main():
     for name in args.cases.split(','):
         mk, cin, h, w = CASES[name]
         torch.manual_seed(0)
-        plan = Plan(mk().eval(), h, w, cin, dev, Config(precision='bf16'), out_dtype=None if args.f32_out else BF16, out_pad=1)
+        act = BF16X2 if args.precision == 'bf16x3' else BF16
+        plan = Plan(mk().eval(), h, w, cin, dev, Config(precision=args.precision), out_dtype=None if args.f32_out else act, out_pad=1)
         plan.src.buf.t.normal_()
         for _ in range(3):
             plan.run()

@@ -15,7 +15,7 @@ from bench import synth_gop, MODEL, H, W
 dev = torch.device('cuda:0')
 net = models.build_standin(**MODEL)
 gop = G.generate_gop_struct('1_GOP_2')
-codec = FrameCodec(net, H, W, dev, Config(precision='bf16'))
+codec = FrameCodec(net, H, W, dev, Config(precision=sys.argv[2] if len(sys.argv) > 2 else 'bf16x3'))
 clip = synth_gop(3, 3)
 frames = {'frame_%d' % i: planes_to_device(clip[i], dev) for i in range(3)}
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
