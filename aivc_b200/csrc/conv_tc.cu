@@ -293,10 +293,12 @@ int conv_tc1_run(const aivc_conv_op *op, cudaStream_t st);
 int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st);
 
 int conv_tc_run(const aivc_conv_op *op, cudaStream_t st) {
-    if (op->engine != AIVC_ENGINE_TC_X3) {                   // (split-bf16 operands: 3x3 persistent kernel or generic)
-        int r = conv_tc1_run(op, st);                        // persistent 1x1 kernel
+    if (op->engine != AIVC_ENGINE_TC_X3) {                   // (plain bf16 only)
+        const int r = conv_tc1_run(op, st);                  // persistent 1x1 kernel
         if (r >= 0) return r;
-        r = tconv_tc3_run(op, st);                           // persistent transposed 3x3 kernel
+    }
+    {
+        const int r = tconv_tc3_run(op, st);                 // persistent transposed 3x3 kernel
         if (r >= 0) return r;
     }
     {

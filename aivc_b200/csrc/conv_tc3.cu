@@ -733,7 +733,9 @@ __device__ __forceinline__ void border_store_up_bf16x32(const Tc3Params *p, int 
         }
 }
 
-template <int ACT>
+// X3 (split-bf16 output): every 32-channel chunk leaves as TWO tiles through the same staging buffer -- the hi halves
+// at channel j0, then the lo halves at channel (c_stride / 2) + j0 of the output pixel.
+template <int ACT, bool X3>
 __device__ __forceinline__ void tconv_epilogue(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
                                                const float *sbias, uint64_t *acc_full, uint64_t *acc_empty,
                                                uint32_t tmem_base, int warp, int lane) {
@@ -772,35 +774,49 @@ __device__ __forceinline__ void tconv_epilogue(const Tc3Params &p, const CUtenso
                     tc_fence_before();
                     mbar_arrive(&acc_empty[step]);
                 }
+                const int oy = 2 * iy + step, ox = 2 * ix + sub;
+                const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
                 if (j0 < p.cout) {
-                    epi_bias_act16<ACT>(v, sbias, j0, 0);
-                    epi_bias_act16<ACT>(v + 16, sbias, j0 + 16, 0);
-                    uint4 o4[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * k + 2 * q], v[8 * k + 2 * q + 1]);
-                            w[q] = *reinterpret_cast<const uint32_t *>(&b2);
-                        }
-                        o4[k] = make_uint4(w[0], w[1], w[2], w[3]);
-                        uint32_t off = (uint32_t)(row * 64 + k * 16);
-                        off ^= ((off >> 7) & 3u) << 4;          // 64B swizzle, as the TMA store expects
-                        *reinterpret_cast<uint4 *>(my_stage + off) = o4[k];
-                    }
-                    const int oy = 2 * iy + step, ox = 2 * ix + sub;
-                    if (valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1))
-                        border_store_up_bf16x32(&p, j0, oy, ox, o4[0], o4[1], o4[2], o4[3]);
+                    epi_bias_act16<ACT>(v, sbias, j0, 0, X3);
+                    epi_bias_act16<ACT>(v + 16, sbias, j0 + 16, 0, X3);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                named_bar_sync(1 + team, 128);
-                if (leader && j0 < p.cout) {
-                    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                                     (uint64_t)tmO),
-                                 "r"(smem_u32(my_stage)), "r"(j0), "r"(sub), "r"(x0), "r"(step), "r"(y0)
-                                 : "memory");
-                    tma_store_commit();
+#pragma unroll 1
+                for (int half = 0; half < (X3 ? 2 : 1); ++half) {
+                    if (half == 1) {                           // the hi tile must have been read before lo overwrites it
+                        if (leader) tma_store_wait_read();
+                        named_bar_sync(1 + team, 128);
+                    }
+                    if (j0 < p.cout) {
+                        uint4 o4[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float a = v[8 * k + 2 * q], b = v[8 * k + 2 * q + 1];
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+                                if (X3 && half == 0) {         // keep the remainder for the lo pass
+                                    const float2 hf = __bfloat1622float2(b2);
+                                    v[8 * k + 2 * q] = a - hf.x; v[8 * k + 2 * q + 1] = b - hf.y;
+                                }
+                                w[q] = *reinterpret_cast<const uint32_t *>(&b2);
+                            }
+                            o4[k] = make_uint4(w[0], w[1], w[2], w[3]);
+                            uint32_t off = (uint32_t)(row * 64 + k * 16);
+                            off ^= ((off >> 7) & 3u) << 4;      // 64B swizzle, as the TMA store expects
+                            *reinterpret_cast<uint4 *>(my_stage + off) = o4[k];
+                        }
+                        if (edge) border_store_up_bf16x32(&p, j0 + half * (p.out.c_stride >> 1), oy, ox, o4[0], o4[1], o4[2], o4[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    named_bar_sync(1 + team, 128);
+                    if (leader && j0 < p.cout) {
+                        asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                                         (uint64_t)tmO),
+                                     "r"(smem_u32(my_stage)), "r"(j0 + half * (p.out.c_stride >> 1)), "r"(sub), "r"(x0), "r"(step), "r"(y0)
+                                     : "memory");
+                        tma_store_commit();
+                    }
                 }
                 store_pending = true;
             }
@@ -826,6 +842,7 @@ tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t *stage = g_ring + (size_t)p.ng * g_slot;          // 4 teams x 8 KB
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.cout;
+    const int nparts = p.x3 ? 3 : 1, npatch = p.x3 ? 2 * p.kchunks : p.kchunks;      // (npatch <= TC_NA)
 
     if (tid == 0) {
         for (int s = 0; s < TC_NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -851,23 +868,26 @@ tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
             for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x) {
                 const int y0 = (tile / p.tiles_x) * 16, x0 = (tile % p.tiles_x) * TILE_W;
-                for (int kc = 0; kc < p.kchunks; ++kc) {      // both chunks' patches stay for the whole tile
+                // all patches of the tile stay for the whole tile: the kchunks hi chunks, then (split-bf16) the lo chunks
+                for (int pi = 0; pi < npatch; ++pi) {
+                    const int kc = pi % p.kchunks;
                     mbar_wait(&a_empty[sa], pa ^ 1u);
                     mbar_expect_tx(&a_full[sa], PATCH_BYTES);
-                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], kc * 64, x0, y0);
+                    tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], kc * 64 + (pi >= p.kchunks ? p.a_lo : 0), x0, y0);
                     if (++sa == TC_NA) { sa = 0; pa ^= 1u; }
                 }
                 for (int g = 0; g < 3; ++g)                    // group 0 = step A, groups 1, 2 = step B
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        if (g == 2 && kc == 0) { /* order: (g1,kc0) (g1,kc1) (g2,kc0) (g2,kc1) */ }
-                        mbar_wait(&g_empty[sg], pg ^ 1u);
-                        mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
-                        uint8_t *dst = g_ring + sg * g_slot;
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        for (int part = 0; part < nparts; ++part) {     // hi.Whi, lo.Whi, hi.Wlo
+                            mbar_wait(&g_empty[sg], pg ^ 1u);
+                            mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
+                            uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
-                        for (int t = 0; t < 3; ++t)
-                            tma_load_3d(dst + t * p.b_slot, &tmB, &g_full[sg], kc * 64, 0, c_tconv3_taps[g * 3 + t].widx);
-                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
-                    }
+                            for (int t = 0; t < 3; ++t)
+                                tma_load_3d(dst + t * p.b_slot, &tmB, &g_full[sg], kc * 64 + (part == 2 ? p.b_lo : 0), 0,
+                                            c_tconv3_taps[g * 3 + t].widx);
+                            if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
+                        }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -876,49 +896,53 @@ tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint64_t a_tmpl = (1ull << 16) | ((uint64_t)((PATCH_W * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
             for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x, ++it) {
-                uint32_t a_addr[2];
+                uint32_t a_addr[TC_NA];
                 const uint32_t sa0 = sa, pa0 = pa;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    a_addr[kc] = smem_u32(a_ring + sa * A_SLOT);
+                for (int pi = 0; pi < npatch; ++pi) {
+                    a_addr[pi] = smem_u32(a_ring + sa * A_SLOT);
                     if (++sa == TC_NA) { sa = 0; pa ^= 1u; }
                 }
                 uint32_t started = 0;                          // phases whose region already holds a partial sum
+                uint32_t waited = 0;                           // patches of this tile whose arrival has been waited for
                 for (int g = 0; g < 3; ++g) {
                     if (g == 0 || g == 1) {                    // a new step starts: its regions must be drained
                         mbar_wait(&acc_empty[g], (it & 1u) ^ 1u);
                         tc_fence_after();
                     }
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        if (g == 0) {                          // first use of this chunk's patch
-                            uint32_t s_ = sa0 + kc, p_ = pa0;
-                            if (s_ >= TC_NA) { s_ -= TC_NA; p_ ^= 1u; }
-                            mbar_wait(&a_full[s_], p_);
-                        }
-                        mbar_wait(&g_full[sg], pg);
-                        tc_fence_after();
-                        const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        for (int part = 0; part < nparts; ++part) {
+                            const int pi = kc + (part == 1 ? p.kchunks : 0);      // hi patch, except for lo.Whi
+                            if (!((waited >> pi) & 1u)) {      // first use of this patch
+                                uint32_t s_ = sa0 + (uint32_t)pi, p_ = pa0;
+                                if (s_ >= TC_NA) { s_ -= TC_NA; p_ ^= 1u; }
+                                mbar_wait(&a_full[s_], p_);
+                                waited |= 1u << pi;
+                            }
+                            mbar_wait(&g_full[sg], pg);
+                            tc_fence_after();
+                            const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const TapT tp = c_tconv3_taps[g * 3 + t];
-                            const uint64_t bdesc = make_desc(g_addr + t * p.b_slot, 128);
-                            const uint32_t start = a_addr[kc] + (uint32_t)(tp.ay * PATCH_W + tp.ax) * 128u;
-                            const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
-                            const uint32_t acc = tmem_base + (uint32_t)tp.ph * 128u;
-                            const uint32_t had = (started >> tp.ph) & 1u;
+                            for (int t = 0; t < 3; ++t) {
+                                const TapT tp = c_tconv3_taps[g * 3 + t];
+                                const uint64_t bdesc = make_desc(g_addr + t * p.b_slot, 128);
+                                const uint32_t start = a_addr[pi] + (uint32_t)(tp.ay * PATCH_W + tp.ax) * 128u;
+                                const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
+                                const uint32_t acc = tmem_base + (uint32_t)tp.ph * 128u;
+                                const uint32_t had = (started >> tp.ph) & 1u;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, had | (uint32_t)kk);
-                            started |= 1u << tp.ph;
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, had | (uint32_t)kk);
+                                started |= 1u << tp.ph;
+                            }
+                            umma_commit(&g_empty[sg]);
+                            if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                         }
-                        umma_commit(&g_empty[sg]);
-                        if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
-                    }
                     if (g == 0) umma_commit(&acc_full[0]);     // step A complete
                 }
                 umma_commit(&acc_full[1]);                     // step B complete
                 {                                              // the tile's patches are free
                     uint32_t s_ = sa0;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int pi = 0; pi < npatch; ++pi) {
                         umma_commit(&a_empty[s_]);
                         if (++s_ == TC_NA) s_ = 0;
                     }
@@ -926,11 +950,20 @@ tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else {
-        switch (p.act) {
-            case AIVC_ACT_LEAKY: tconv_epilogue<AIVC_ACT_LEAKY>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_RELU: tconv_epilogue<AIVC_ACT_RELU>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
-            case AIVC_ACT_SIGMOID: tconv_epilogue<AIVC_ACT_SIGMOID>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
-            default: tconv_epilogue<AIVC_ACT_NONE>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+        if (p.x3) {
+            switch (p.act) {
+                case AIVC_ACT_LEAKY: tconv_epilogue<AIVC_ACT_LEAKY, true>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                case AIVC_ACT_RELU: tconv_epilogue<AIVC_ACT_RELU, true>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                case AIVC_ACT_SIGMOID: tconv_epilogue<AIVC_ACT_SIGMOID, true>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                default: tconv_epilogue<AIVC_ACT_NONE, true>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+            }
+        } else {
+            switch (p.act) {
+                case AIVC_ACT_LEAKY: tconv_epilogue<AIVC_ACT_LEAKY, false>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                case AIVC_ACT_RELU: tconv_epilogue<AIVC_ACT_RELU, false>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                case AIVC_ACT_SIGMOID: tconv_epilogue<AIVC_ACT_SIGMOID, false>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+                default: tconv_epilogue<AIVC_ACT_NONE, false>(p, &tmO, stage, sbias, acc_full, acc_empty, tmem_base, warp, lane); break;
+            }
         }
     }
 
@@ -1063,13 +1096,15 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
 // Transposed 3x3 stride-2 stage on the persistent kernel above; -1 = not eligible.
 int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int cin = op->in.c, cout = op->out.c;
+    const bool x3 = op->engine == AIVC_ENGINE_TC_X3;         // split-bf16 operands and output
     if (op->kind != 1 || op->k != 3 || op->stride != 2) return -1;
     if (cin % 64 || cin > 128 || cout % 32 || cout > 128) return -1;
     if (op->act == AIVC_ACT_GDN || op->act == AIVC_ACT_IGDN || op->act_channels) return -1;
     if (op->residual.data || op->gate.data || op->out_scale || op->post != AIVC_POST_NONE) return -1;
     const aivc_fmap &in = op->in, &o = op->out;
-    if (in.dtype != AIVC_BF16 || in.c_off % 8 || in.c_stride % 8) return -1;
-    if (o.dtype != AIVC_BF16 || o.c_off % 8 || o.c_stride % 8 || ((uintptr_t)o.data & 15)) return -1;
+    const int dt = x3 ? AIVC_BF16X2 : AIVC_BF16, al = x3 ? 16 : 8;
+    if (in.dtype != dt || in.c_off % 8 || in.c_stride % al) return -1;
+    if (o.dtype != dt || o.c_off % 8 || o.c_stride % al || ((uintptr_t)o.data & 15)) return -1;
     const int tiles_x = ceil_div(in.w, TILE_W), ntiles = tiles_x * ceil_div(in.h, 16);
     if (ntiles < 120) return -1;                            // tiny maps: the phase-parallel generic kernel fills the chip better
 
@@ -1078,6 +1113,7 @@ int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.out = to_dev(o);
     p.bias = op->bias;
     p.cout = cout; p.ncta = cout; p.nsplit = 1; p.kchunks = cin / 64;
+    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? 3 : 1) * p.kchunks; p.a_lo = in.c_stride / 2; p.b_lo = cin;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles;
     p.b_bytes = (uint32_t)cout * 128u;
@@ -1088,21 +1124,22 @@ int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     CUtensorMap tmA, tmB, tmO;
     const size_t pix_b = (size_t)in.c_stride * 2, row_b = (size_t)in.pitch * pix_b;
     {   // interior only: rows / columns beyond the image read as zero (the transposed conv's padding)
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)in.w, (cuuint64_t)in.h};
+        cuuint64_t dims[3] = {(cuuint64_t)(x3 ? p.a_lo + cin : cin), (cuuint64_t)in.w, (cuuint64_t)in.h};
         cuuint64_t strides[2] = {pix_b, row_b};
         cuuint32_t box[3] = {64, PATCH_W, 18};
         void *base = (char *)in.data + ((size_t)in.pad * in.pitch + in.pad) * pix_b + (size_t)in.c_off * 2;
         if (encode_map(&tmA, base, 3, dims, strides, box, 128, "A/tconv3")) return 1;
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
-        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+        const int wcin = x3 ? 2 * cin : cin;                   // x3: [tap][cout][hi cin | lo cin]
+        cuuint64_t dims[3] = {(cuuint64_t)wcin, (cuuint64_t)cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)wcin * 2, (cuuint64_t)wcin * cout * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)cout, 1};
         if (encode_map(&tmB, (void *)op->weight, 3, dims, strides, box, 128, "B/tconv3")) return 1;
     }
     {   // output interior as (c, x parity, x/2, y parity, y/2): one phase of a tile is a {32, 1, 8, 1, 16} box
         const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
-        cuuint64_t dims[5] = {(cuuint64_t)cout, 2, (cuuint64_t)in.w, 2, (cuuint64_t)in.h};
+        cuuint64_t dims[5] = {(cuuint64_t)(x3 ? o.c_stride / 2 + cout : cout), 2, (cuuint64_t)in.w, 2, (cuuint64_t)in.h};
         cuuint64_t strides[4] = {opix, 2 * opix, orow, 2 * orow};
         cuuint32_t box[5] = {32, 1, TILE_W, 1, 16};
         void *base = (char *)o.data + ((size_t)o.pad * o.pitch + o.pad) * opix + (size_t)o.c_off * 2;

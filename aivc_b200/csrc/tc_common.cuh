@@ -363,9 +363,10 @@ __device__ __forceinline__ void unpack_bf16x16(const uint4 *rb, float *r) {
 __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const float *sscale, int oy, int ox,
                                            int j0, bool interior, size_t out_elem, const uint4 *rb = nullptr,
                                            const uint4 *gb = nullptr) {
-    if (gb) {                       // gate row prefetched as packed bf16
+    if (gb) {                       // gate row prefetched as packed bf16 (split maps: [2..3] = the lo halves)
         float g[16];
         unpack_bf16x16(gb, g);
+        if (c.gate.dtype == AIVC_BF16X2) { add_packed_bf16x8(g, gb[2]); add_packed_bf16x8(g + 8, gb[3]); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= g[i];
     } else if (c.gate.data) {
@@ -377,6 +378,7 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
     if (rb) {                       // residual row prefetched as packed bf16 (see res_prefetch)
         float r[16];
         unpack_bf16x16(rb, r);
+        if (c.res.dtype == AIVC_BF16X2) { add_packed_bf16x8(r, rb[2]); add_packed_bf16x8(r + 8, rb[3]); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
     } else if (c.res.data) {
@@ -401,35 +403,46 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
     else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
 }
 
+template <bool X2 = false>
 __device__ __forceinline__ void fetch16(const FMap &m, size_t elem, int j0, uint4 *rb) {
     const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0);
     rb[0] = p[0];
     rb[1] = p[1];
+    if (X2 && m.dtype == AIVC_BF16X2) {                        // lo halves of a split map
+        const uint4 *pl = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0 + (m.c_stride >> 1));
+        rb[2] = pl[0];
+        rb[3] = pl[1];
+    }
 }
 
-template <int ACT>
+// X2PIPE: also pipeline split-bf16 residual / gate rows (8 more registers per row in flight: only kernels with
+// registers to spare -- the generic kernel -- ask for it; the 96-register persistent kernels load split rows in place)
+template <int ACT, bool X2PIPE = false>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
                                         const EpiCtx &c, int oy, int ox, bool valid, int c_begin = 0) {
     const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
     const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
     // bf16 residual / gate rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
     // the TMEM load and arithmetic of chunk j
-    const bool pipe_res = valid && c.res.data && c.res_vec && c.res.dtype == AIVC_BF16;
-    const bool pipe_gate = valid && c.gate.data && c.gate_vec && c.gate.dtype == AIVC_BF16;
+    constexpr int NB = X2PIPE ? 4 : 2;
+    const bool pipe_res = valid && c.res.data && c.res_vec && (c.res.dtype == AIVC_BF16 || (X2PIPE && c.res.dtype == AIVC_BF16X2));
+    const bool pipe_gate = valid && c.gate.data && c.gate_vec && (c.gate.dtype == AIVC_BF16 || (X2PIPE && c.gate.dtype == AIVC_BF16X2));
     const size_t res_elem = pipe_res ? fm_index(c.res, oy, ox, 0) : 0;
     const size_t gate_elem = pipe_gate ? fm_index(c.gate, oy, ox, 0) : 0;
-    uint4 rb[2], rn[2], gb[2], gn[2];
-    if (pipe_res) fetch16(c.res, res_elem, c_begin, rn);
-    if (pipe_gate) fetch16(c.gate, gate_elem, c_begin, gn);
+    uint4 rb[NB], rn[NB], gb[NB], gn[NB];
+    if (pipe_res) fetch16<X2PIPE>(c.res, res_elem, c_begin, rn);
+    if (pipe_gate) fetch16<X2PIPE>(c.gate, gate_elem, c_begin, gn);
 #pragma unroll 1
     for (int j0 = c_begin; j0 < N; j0 += 16) {
         if (pipe_res) {
-            rb[0] = rn[0]; rb[1] = rn[1];
-            if (j0 + 16 < N) fetch16(c.res, res_elem, j0 + 16, rn);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) rb[i] = rn[i];
+            if (j0 + 16 < N) fetch16<X2PIPE>(c.res, res_elem, j0 + 16, rn);
         }
         if (pipe_gate) {
-            gb[0] = gn[0]; gb[1] = gn[1];
-            if (j0 + 16 < N) fetch16(c.gate, gate_elem, j0 + 16, gn);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) gb[i] = gn[i];
+            if (j0 + 16 < N) fetch16<X2PIPE>(c.gate, gate_elem, j0 + 16, gn);
         }
         float v[16];
         tmem_ld16(taddr + (uint32_t)j0, v);
@@ -443,10 +456,10 @@ __device__ __forceinline__ void epi_row_dispatch(int act, uint32_t taddr, int N,
                                                  bool valid, int c_begin = 0) {
     // channels [c_begin, N)
     switch (act) {
-        case AIVC_ACT_LEAKY: epi_row<AIVC_ACT_LEAKY>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
-        case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
-        case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
-        default: epi_row<AIVC_ACT_NONE>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        case AIVC_ACT_LEAKY: epi_row<AIVC_ACT_LEAKY, true>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        case AIVC_ACT_RELU: epi_row<AIVC_ACT_RELU, true>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        case AIVC_ACT_SIGMOID: epi_row<AIVC_ACT_SIGMOID, true>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
+        default: epi_row<AIVC_ACT_NONE, true>(taddr, N, sbias, sscale, c, oy, ox, valid, c_begin); break;
     }
 }
 
