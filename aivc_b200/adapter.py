@@ -14,8 +14,10 @@
 ``decode_video(model, video_bytes)`` is decode_one_video (real_life/decode.py:44-154) without
 the temp-dir round trips: bytes in, decoded uint8 planes out.
 """
+import collections
 import os
 import pickle
+import weakref
 
 import numpy as np
 import torch
@@ -25,16 +27,28 @@ from .codec import FrameCodec, latent_dims
 from .gop import generate_gop_struct, FRAME_I
 from .plan import Config
 
+_CODECS = weakref.WeakKeyDictionary()        # model -> OrderedDict(key -> (weights version, FrameCodec)), LRU
+MAX_CODECS_PER_MODEL = 2                     # a 1080p codec holds 3-6 GB of plans and buffers
+
+
 def codec_for(model, h, w, device, cfg=None, idx_rate=0.):
-    """FrameCodec of `model` for this frame size, cached ON the model (a cache keyed by id(model) would hand
-    a dead model's codec to a new model that happens to reuse the address)."""
+    """FrameCodec of `model` for this frame size / device / config / rate index.  Cached per model object in a
+    WeakKeyDictionary (not in `model.__dict__`: whole-module pickles and deepcopies stay clean; not by id(model): a
+    dead model's codec is never handed to a new model at the same address), rebuilt when the model's weights have
+    changed since they were packed, at most MAX_CODECS_PER_MODEL alive per model (least recently used goes)."""
+    from .plan import weights_version
     cfg = cfg or Config()
-    cache = model.__dict__.setdefault('_aivc_b200_codecs', {})
+    cache = _CODECS.setdefault(model, collections.OrderedDict())
     key = (h, w, str(device), cfg.key(), float(idx_rate))
-    c = cache.get(key)
-    if c is None:
-        c = cache[key] = FrameCodec(model, h, w, device, cfg, idx_rate)
-    return c
+    ver = weights_version(model)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:
+        cache.pop(key, None)
+        while len(cache) >= MAX_CODECS_PER_MODEL:
+            cache.popitem(last=False)
+        hit = cache[key] = (ver, FrameCodec(model, h, w, device, cfg, idx_rate))
+    cache.move_to_end(key)
+    return hit[1]
 
 
 def _to_planes(yuv, device):

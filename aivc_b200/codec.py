@@ -319,7 +319,7 @@ class FrameCodec:
                                                  _lib.stream_ptr()))
 
     def _fusable(self, *frames):
-        return self.cfg.precision == 'bf16' and all(f is None or f[0].dtype == torch.uint8 for f in frames)
+        return self.levels and all(f is None or f[0].dtype == torch.uint8 for f in frames)
 
     def _zero_pred(self):
         self.codec_in.zero_channels(3, 6)

@@ -10,6 +10,7 @@
   convert(model)   -- swaps reference layer instances of an already loaded model for mirrors
                       (weights shared, not copied), so every ``forward`` runs the CUDA path.
 """
+import os
 import sys
 import types
 
@@ -90,7 +91,12 @@ def install():
         _orig = torch.load
 
         def load(*a, **k):
-            k.setdefault('weights_only', False)     # AIVC checkpoints are whole-module pickles
+            # AIVC checkpoints are whole-module pickles (model_management.py:347 calls torch.load(path, map_location=..)).
+            # Only THAT call site -- and callers that set AIVC_B200_TRUST_PICKLES=1 -- get the unsafe default back;
+            # everybody else keeps torch's weights_only=True.
+            caller = sys._getframe(1).f_globals.get('__name__', '')
+            if caller.endswith('model_management') or os.environ.get('AIVC_B200_TRUST_PICKLES') == '1':
+                k.setdefault('weights_only', False)
             return _orig(*a, **k)
         load._aivc_patched = True
         torch.load = load

@@ -130,13 +130,17 @@ __global__ void yuv420_pack16_kernel(PackSrc s, FMap dst, FMap dst2) {
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
             return *reinterpret_cast<const uint32_t *>(&b2);
         };
+        // (split-bf16 buffers: 8-bit levels are exact in the hi half, the lo half of the 32-element pixel is zero)
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)dst.data + ((size_t)py * dst.pitch + px) * dst.c_stride);
         q[0] = make_uint4(pk(c[0], c[1]), pk(c[2], c[3]), pk(c[4], c[5]), pk(c[6], c[7]));
         q[1] = make_uint4(pk(c[8], 0.f), 0u, 0u, 0u);
+        if (dst.dtype == AIVC_BF16X2) { q[2] = zero; q[3] = zero; }
         if (dst2.data) {
             uint4 *q2 = reinterpret_cast<uint4 *>((__nv_bfloat16 *)dst2.data + ((size_t)py * dst2.pitch + px) * dst2.c_stride);
             q2[0] = make_uint4(pk(c[0], c[1]), pk(c[2], 0.f), 0u, 0u);
-            q2[1] = make_uint4(0u, 0u, 0u, 0u);
+            q2[1] = zero;
+            if (dst2.dtype == AIVC_BF16X2) { q2[2] = zero; q2[3] = zero; }
         }
     }
 }
@@ -183,9 +187,11 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
     const int h = pred.h, w = pred.w;
     const size_t n = (size_t)h * w;
     // both references are channel slices 3..5 / 6..8 of ONE 16-channel bf16 pixel buffer (the bf16 engine's mof_in)
-    const bool fast = prev.dtype == AIVC_BF16 && next.dtype == AIVC_BF16 && prev.data == next.data && prev.c_stride == 16 &&
-                      prev.c_off == 3 && next.c_off == 6 && prev.pad == next.pad && prev.pitch == next.pitch &&
-                      ((uintptr_t)prev.data & 15) == 0;
+    const bool x2 = prev.dtype == AIVC_BF16X2;                 // split-bf16 pixel: 16 hi + 16 lo elements
+    const bool fast = (prev.dtype == AIVC_BF16 || x2) && next.dtype == prev.dtype && prev.data == next.data &&
+                      prev.c_stride == (x2 ? 32 : 16) && prev.c_off == 3 && next.c_off == 6 && prev.pad == next.pad &&
+                      prev.pitch == next.pitch && ((uintptr_t)prev.data & 15) == 0;
+    const int pix_elems = x2 ? 32 : 16;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(i / w), x = (int)(i % w);
@@ -204,18 +210,28 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
             // 16-channel level-unit pixels (prev = channels 3..5, next = 6..8 of the same 32-byte pixel):
             // one 16-byte load per prev corner, an 8- and a 4-byte load per next corner
             const __nv_bfloat16 *base = (const __nv_bfloat16 *)prev.data;
-            auto pix = [&](int yy, int xx) { return base + ((size_t)(yy + prev.pad) * prev.pitch + (xx + prev.pad)) * 16; };
+            auto pix = [&](int yy, int xx) { return base + ((size_t)(yy + prev.pad) * prev.pitch + (xx + prev.pad)) * pix_elems; };
             auto hi16 = [](uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); };
             auto lo16 = [](uint32_t v) { return __uint_as_float(v << 16); };
             a3[0] = a3[1] = a3[2] = b3[0] = b3[1] = b3[2] = 0.f;
             auto tap_prev = [&](int yy, int xx, float wgt) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(pix(yy, xx));          // channels 0..7
-                a3[0] += hi16(v.y) * wgt; a3[1] += lo16(v.z) * wgt; a3[2] += hi16(v.z) * wgt;
+                float c0 = hi16(v.y), c1 = lo16(v.z), c2 = hi16(v.z);
+                if (x2) {                                                               // + lo halves
+                    const uint4 l = *reinterpret_cast<const uint4 *>(pix(yy, xx) + 16);
+                    c0 += hi16(l.y); c1 += lo16(l.z); c2 += hi16(l.z);
+                }
+                a3[0] += c0 * wgt; a3[1] += c1 * wgt; a3[2] += c2 * wgt;
             };
             auto tap_next = [&](int yy, int xx, float wgt) {
                 const __nv_bfloat16 *q = pix(yy, xx);
                 const uint32_t c67 = *reinterpret_cast<const uint32_t *>(q + 6), c89 = *reinterpret_cast<const uint32_t *>(q + 8);
-                b3[0] += lo16(c67) * wgt; b3[1] += hi16(c67) * wgt; b3[2] += lo16(c89) * wgt;
+                float c0 = lo16(c67), c1 = hi16(c67), c2 = lo16(c89);
+                if (x2) {
+                    const uint32_t l67 = *reinterpret_cast<const uint32_t *>(q + 22), l89 = *reinterpret_cast<const uint32_t *>(q + 24);
+                    c0 += lo16(l67); c1 += hi16(l67); c2 += lo16(l89);
+                }
+                b3[0] += c0 * wgt; b3[1] += c1 * wgt; b3[2] += c2 * wgt;
             };
             tap_prev(bp.y0, bp.x0, bp.w00);
             if (bp.x1 < w) tap_prev(bp.y0, bp.x1, bp.w01);
@@ -621,13 +637,14 @@ int aivc_yuv420_pack16(const void *y0, const void *u0, const void *v0, const voi
                        const void *v1, const void *y2, const void *u2, const void *v2, const aivc_fmap *dst,
                        const aivc_fmap *dst2, void *stream) {
     if (validate_fmap(dst, "yuv420_pack16 dst")) return 1;
-    if (dst->dtype != AIVC_BF16 || dst->c_stride != 16 || dst->c_off != 0 || ((uintptr_t)dst->data & 15))
-        AIVC_FAIL("yuv420_pack16: destination must be a whole 16-channel bf16 pixel buffer");
+    const bool x2 = dst->dtype == AIVC_BF16X2;
+    if ((dst->dtype != AIVC_BF16 && !x2) || dst->c_stride != (x2 ? 32 : 16) || dst->c_off != 0 || ((uintptr_t)dst->data & 15))
+        AIVC_FAIL("yuv420_pack16: destination must be a whole 16-channel (split-)bf16 pixel buffer");
     FMap d2;
     memset(&d2, 0, sizeof(d2));
     if (dst2) {
         if (validate_fmap(dst2, "yuv420_pack16 dst2")) return 1;
-        if (dst2->dtype != AIVC_BF16 || dst2->c_stride != 16 || dst2->c_off != 0 || dst2->h != dst->h || dst2->w != dst->w ||
+        if (dst2->dtype != dst->dtype || dst2->c_stride != dst->c_stride || dst2->c_off != 0 || dst2->h != dst->h || dst2->w != dst->w ||
             dst2->pad != dst->pad || ((uintptr_t)dst2->data & 15))
             AIVC_FAIL("yuv420_pack16: second destination must match the first");
         d2 = to_dev(*dst2);

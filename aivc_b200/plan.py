@@ -19,6 +19,7 @@ recycled by liveness.  All stages of a plan run with ONE ctypes call
 (``aivc_conv2d_fused_seq``) on the current CUDA stream.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -541,7 +542,25 @@ class Plan:
 
 
 # ------------------------------------------------------------------ nn.Module boundary
-_CACHE_ATTR = '_aivc_b200_plans'
+# Plans of a module, per input geometry.  Kept OUT of the module (a WeakKeyDictionary keyed by the module object): the
+# reference stores whole-module pickles, and `torch.save(model)` / `copy.deepcopy(model)` must not meet ctypes arrays
+# with device pointers in `module.__dict__`; the entry dies with the module, so a recycled id() cannot alias it.
+_PLANS = weakref.WeakKeyDictionary()
+
+
+def cached_plans(module):
+    return _PLANS.setdefault(module, {})
+
+
+def weights_version(module):
+    """Changes whenever a parameter or buffer of `module` is modified in place (load_state_dict, optimiser step,
+    manual edits under no_grad): packed weights of a cached plan are then stale."""
+    v = 0
+    for t in module.parameters():
+        v += t._version
+    for t in module.buffers():
+        v += t._version
+    return v
 
 
 def run_module(module, x, cfg=DEFAULT):
@@ -554,13 +573,14 @@ def run_module(module, x, cfg=DEFAULT):
     L = _lib.lib()
     x = x.contiguous().float()
     _, c, h, w = x.shape
-    cache = module.__dict__.setdefault(_CACHE_ATTR, {})
+    cache = cached_plans(module)
     key = (h, w, c, x.device.index, cfg.key())
-    plan = cache.get(key)
-    if plan is None:
+    ver = weights_version(module)
+    hit = cache.get(key)
+    if hit is None or hit[0] != ver:              # (weights changed since the plan packed them: lower again)
         with torch.cuda.device(x.device):
-            plan = Plan(module, h, w, c, x.device, cfg)
-        cache[key] = plan
+            hit = cache[key] = (ver, Plan(module, h, w, c, x.device, cfg))
+    plan = hit[1]
     with torch.cuda.device(x.device):
         st = _lib.stream_ptr()
         fin = plan.in_fmap

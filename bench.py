@@ -45,9 +45,10 @@ def set_workload(name, seed=None):
         MODEL = dict(MODEL, seed=seed)
 
 
-def synth_gop(seed, n_frames, h=H, w=W):
+def synth_gop(seed, n_frames, h=None, w=None):
     """Seeded synthetic 4:2:0 clip: low-pass noise texture translated by (2t, t)
     pixels per frame plus 5% fresh noise, 8-bit."""
+    h, w = h or H, w or W                      # (the workload's size at call time)
     rng = np.random.default_rng(seed)
     import torch
     import torch.nn.functional as F

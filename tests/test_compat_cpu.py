@@ -206,7 +206,15 @@ def test_sitecustomize_is_subprocess_safe_and_loads_whole_module_pickles(tmp_pat
     code = ('import torch, torchac, models, layers.misc.misc_layers as ml, layers.entropy_coding.entropy_coder as ec\n'
             'from layers.entropy_coding.pdf_estimator import ParametricPdf, BallePdfEstim\n'
             'assert hasattr(torch, "set_deterministic") and hasattr(ml, "View") and hasattr(ml, "LowerBound")\n'
-            'm = torch.load("0_model.pt", map_location="cpu")\n'
+            '# the unsafe whole-module unpickling is scoped to the reference\'s own call site (model_management.py:347)\n'
+            'import types, pickle\n'
+            'mm = types.ModuleType("model_mngt.model_management"); mm.torch = torch\n'
+            'exec("def load_model(p):\\n    return torch.load(p, map_location=\'cpu\')", mm.__dict__)\n'
+            'try:\n'
+            '    torch.load("0_model.pt", map_location="cpu"); raise SystemExit("plain torch.load must stay weights_only")\n'
+            'except pickle.UnpicklingError:\n'
+            '    pass\n'
+            'm = mm.load_model("0_model.pt")\n'
             'cn = m.codec_net.codec_net\n'
             'assert type(m).__module__ == "aivc_b200.models" and type(cn.g_a[0]).__module__ == "aivc_b200.layers"\n'
             'assert hasattr(m, "GOP_forward") and cn.nb_ft_y == 8 and isinstance(cn.pdf_y, ParametricPdf)\n'

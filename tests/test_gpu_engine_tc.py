@@ -36,7 +36,7 @@ def _check(y, ref, rms_tol, max_tol=0.06):
 def _uses_tc(m, x):
     from aivc_b200 import plan
     from aivc_b200._lib import ENGINE_TC
-    p = next(iter(m.__dict__[plan._CACHE_ATTR].values()))
+    p = next(iter(plan.cached_plans(m).values()))[1]
     return sum(1 for s in p.stages if s.engine == ENGINE_TC), len(p.stages)
 
 

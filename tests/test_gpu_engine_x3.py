@@ -68,7 +68,7 @@ def test_wide_layers_x3_vs_oracle(name, size, dev):
     with torch.no_grad():
         ref = R.forward_module(m, x).numpy()
     y = plan.run_module(m, x.to(dev), _cfg()).cpu().numpy()
-    p = next(iter(m.__dict__[plan._CACHE_ATTR].values()))
+    p = next(iter(plan.cached_plans(m).values()))[1]
     assert all(s.engine == ENGINE_TC_X3 for s in p.stages), [s.engine for s in p.stages]
     assert y.shape == ref.shape
     _check(y, ref)

@@ -193,8 +193,9 @@ def test_oracle_decodes_gpu_bitstream(golden_dir, dev):
             assert np.array_equal(got, p.cpu().numpy()), (f, k)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
 @pytest.mark.parametrize('size', [(135, 241), (240, 416)])
-def test_closed_loop_odd_and_reference_sizes(size, dev):
+def test_closed_loop_odd_and_reference_sizes(size, precision, dev):
     """Edge geometry: odd luma/chroma sizes, ceil-halving latents. Property:
     decode(encode(x)) reproduces the encoder's reconstruction exactly, for I, P and B."""
     from aivc_b200 import models, gop as G
@@ -209,7 +210,7 @@ def test_closed_loop_odd_and_reference_sizes(size, dev):
         y = rng.integers(0, 256, (h, w), dtype=np.uint8)
         u = rng.integers(0, 256, ((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
         frames['frame_%d' % t] = planes_to_device([y, u, 255 - u], dev)
-    codec = FrameCodec(net, h, w, dev, Config(precision='fp32'))
+    codec = FrameCodec(net, h, w, dev, Config(precision=precision))
     bts, rec = codec.encode_gop(frames, gop)
     dec = codec.decode_gop(bts, gop)
     for f in gop:
@@ -248,3 +249,30 @@ def test_entropy_model_classes_vs_reference_golden(golden_dir, dev):
     with torch.no_grad():
         p = bz(torch.from_numpy(fx['balle_z']))
     np.testing.assert_allclose(p.numpy(), fx['balle_p'], rtol=1e-6, atol=1e-7)
+
+
+def test_plan_cache_follows_the_weights_and_stays_out_of_the_module(golden_dir, dev, tmp_path):
+    """(1) weights changed after the first forward (load_state_dict, fine-tuning) must not be ignored by the
+    cached plan; (2) after a forward the module is still picklable / deep-copyable (the reference stores whole-module
+    pickles) -- the caches live in a WeakKeyDictionary, not in module.__dict__."""
+    import copy
+    import io
+    from aivc_b200 import plan
+    m, fx = load_leaf('cheng_plain', golden_dir)
+    x = torch.from_numpy(fx['x0']).to(dev)
+    y0 = plan.run_module(m, x, _fp32()).cpu().numpy()
+    np.testing.assert_allclose(y0, fx['y0'], rtol=RTOL, atol=ATOL)
+    assert not any(k.startswith('_aivc') for k in m.__dict__)
+    m2 = copy.deepcopy(m)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(0.5)
+    y1 = plan.run_module(m, x, _fp32()).cpu().numpy()
+    assert np.abs(y1 - y0).max() > 1e-3                      # the new weights are in use
+    y2 = plan.run_module(m2, x, _fp32()).cpu().numpy()       # the copy kept the old ones
+    assert np.array_equal(y2, y0)
+    m.load_state_dict(m2.state_dict())
+    assert np.array_equal(plan.run_module(m, x, _fp32()).cpu().numpy(), y0)
+    assert len(plan.cached_plans(m)) == 1

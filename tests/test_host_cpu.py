@@ -221,3 +221,33 @@ def test_yuv_file_io_roundtrip_and_gop_schedule(tmp_path):
     open(str(tmp_path / 'bad_18x10_30_420.yuv'), 'wb').write(b'123')
     with pytest.raises(ValueError):
         yuvio.YuvReader(str(tmp_path / 'bad_18x10_30_420.yuv'))
+
+
+def test_codec_cache_is_versioned_weak_and_bounded(monkeypatch):
+    """adapter.codec_for: one codec per (size, device, config, rate) and model, rebuilt when the weights change,
+    at most MAX_CODECS_PER_MODEL alive, gone with the model, nothing stored on the model itself."""
+    import gc
+    import torch
+    from aivc_b200 import adapter, models
+    built = []
+
+    class Fake:
+        def __init__(self, model, h, w, device, cfg, idx_rate):
+            built.append((h, w))
+    monkeypatch.setattr(adapter, 'FrameCodec', Fake)
+    net = models.build_standin(seed=1, C=16, Cy=8, Cz=8, Csc=8)
+    a = adapter.codec_for(net, 64, 64, 'cuda:0')
+    assert adapter.codec_for(net, 64, 64, 'cuda:0') is a and len(built) == 1
+    with torch.no_grad():
+        next(net.parameters()).add_(1.0)
+    b = adapter.codec_for(net, 64, 64, 'cuda:0')
+    assert b is not a and len(built) == 2                    # weights changed -> packed weights are stale
+    adapter.codec_for(net, 32, 32, 'cuda:0')
+    adapter.codec_for(net, 16, 16, 'cuda:0')                 # third geometry: the least recently used one goes
+    assert len(adapter._CODECS[net]) == adapter.MAX_CODECS_PER_MODEL
+    assert adapter.codec_for(net, 64, 64, 'cuda:0') is not b
+    assert not any(k.startswith('_aivc') for k in net.__dict__)
+    n = len(adapter._CODECS)
+    del net, a, b
+    gc.collect()
+    assert len(adapter._CODECS) == n - 1

@@ -43,9 +43,9 @@ def main():
                 with torch.no_grad():
                     ref = R.forward_module(m, x.double() if False else x).numpy()
                 y = plan.run_module(m, x.to(dev), cfg).cpu().numpy()
-                p = next(iter(m.__dict__[plan._CACHE_ATTR].values()))
+                p = next(iter(plan.cached_plans(m).values()))[1]
                 eng = [s.engine for s in p.stages]
-                m.__dict__[plan._CACHE_ATTR].clear()
+                plan.cached_plans(m).clear()
                 print('wide %-20s %3dx%-3d rms %.2e max %.2e engines %s' % ((name, h, w) + stats(y, ref) + (eng,)))
         fx = np.load(os.path.join(gd, 'system_80x112.npz'))
         h, w = int(fx['H']), int(fx['W'])
