@@ -333,7 +333,7 @@ class Arm:
             cls = (C.c_double * (3 * ncls))()
             self._lib.check(L.aivc_profile_read_classes(cls, ncls))
             prof = list(out) + list(cls)
-            if self.args.stage_csv and self.rank == 0:
+            if self.args.stage_csv and self.rank == 0 and getattr(self, 'dump_csv', True):
                 self._lib.check(L.aivc_profile_dump(self.args.stage_csv.encode()))
             L.aivc_profile_enable(0)
         codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
@@ -484,6 +484,7 @@ def run_ours(args):
             del arm
             torch.cuda.empty_cache()
             alt = Arm(other, *common)
+            alt.dump_csv = False                      # (--stage-csv holds the headline arm's stages)
             alt.step(False)
             alt.step(False)
             ms_a, _, _, _ = alt.timed(False, False, args.steps)
