@@ -276,3 +276,46 @@ def test_plan_cache_follows_the_weights_and_stays_out_of_the_module(golden_dir, 
     m.load_state_dict(m2.state_dict())
     assert np.array_equal(plan.run_module(m, x, _fp32()).cpu().numpy(), y0)
     assert len(plan.cached_plans(m)) == 1
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
+def test_edge_inputs_empty_latents_and_tiny_frames(precision, dev):
+    """Edge cases of the path (the reference handles them in bitstream.py:241-255, 292-296 and decode.py:562-571):
+    (1) a flat frame whose latents quantise to ALL ZEROS in some nets -- no channel is sent, the y section is the single
+        byte n_ch = 0 and the decoder must rebuild zeros without touching the range coder;
+    (2) the smallest frames the four + two stride-2 stages allow without degenerate maps (18x34: y 2x3, z 1x1) and an odd
+        size in both dimensions (33x47);
+    (3) an all-intra GOP ('1_GOP_0') and a P-only chain ('LDP_3').
+    Property everywhere: decoder == encoder reconstruction, and re-encoding gives the same bytes."""
+    from aivc_b200 import models, gop as G, entropy
+    from aivc_b200.codec import FrameCodec, planes_to_device
+    from aivc_b200.plan import Config
+    net = models.build_standin(seed=11, C=32, Cy=16, Cz=16, Csc=16)
+    rng = np.random.default_rng(2)
+    for (h, w), gop_name in (((18, 34), '1_GOP_2'), ((33, 47), 'LDP_3'), ((48, 64), '1_GOP_0')):
+        gop = G.generate_gop_struct(gop_name)
+        hc, wc = (h + 1) // 2, (w + 1) // 2
+        frames = {}
+        for i, f in enumerate(sorted(gop)):
+            if i == 0:                                   # flat mid-grey frame
+                frames[f] = planes_to_device([np.full((h, w), 128, np.uint8), np.full((hc, wc), 128, np.uint8),
+                                              np.full((hc, wc), 128, np.uint8)], dev)
+            else:
+                frames[f] = planes_to_device([rng.integers(0, 256, (h, w), dtype=np.uint8),
+                                              rng.integers(0, 256, (hc, wc), dtype=np.uint8),
+                                              rng.integers(0, 256, (hc, wc), dtype=np.uint8)], dev)
+        codec = FrameCodec(net, h, w, dev, Config(precision=precision))
+        bts, rec = codec.encode_gop(frames, gop)
+        dec = codec.decode_gop(bts, gop)
+        bts2, _ = codec.encode_gop(frames, gop)
+        assert bts2 == bts
+        for f in gop:
+            secs = entropy.split_sections(bts[f])
+            assert len(secs) == 4
+            for a, b in zip(rec[f], dec[f]):
+                assert torch.equal(a, b), (h, w, gop_name, f)
+    # (1) explicitly: a latent with no non-zero channel is one byte, and decodes to zeros
+    sec = entropy.encode_y(np.zeros((4, 6), np.uint32), np.zeros(4, np.int32))
+    assert sec == (1).to_bytes(4, 'big') + b'\x00'
+    q = entropy.decode_y(sec[4:], np.ones((4, 2, 3), np.float32), 4, 2, 3)
+    assert q.shape == (4, 2, 3) and not q.any()
