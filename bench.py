@@ -382,6 +382,8 @@ def roofline_of(prof, steps, ms_prof, precision, kernel_classes):
     return {
         'bound': 'tensor', 'achieved': ach, 'peak': peak_alg, 'unit': 'TFLOP/s', 'frac': ach / peak_alg,
         'traffic': traffic,
+        # the same numbers in tensor-pipe terms: MMA FLOP/s actually issued against the measured bf16 rate itself
+        'mma_per_flop': mma_per_flop, 'tensor_pipe_tflops': mma_per_flop * ach, 'tensor_pipe_peak': peak_tf,
         'peak_source': peak_src + ('; bf16x3 issues three bf16 MMAs (hi.Whi + lo.Whi + hi.Wlo) per algorithmic multiply-add, so the '
                                    'peak for ALGORITHMIC FLOP/s is the measured bf16 rate / 3 (SURVEY.md 8d: "report against '
                                    'the corresponding peak"); tensor-pipe rate = 3 x achieved = %.0f TFLOP/s of %.0f'
