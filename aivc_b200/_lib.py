@@ -55,6 +55,9 @@ _SIGS = {
     'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 4),
     'aivc_conv2d_fused': (C.c_int, [C.POINTER(ConvOp), C.c_void_p]),
     'aivc_conv2d_fused_seq': (C.c_int, [C.POINTER(ConvOp), C.c_int, C.c_void_p]),
+    'aivc_plan_graph_create': (C.c_int, [C.POINTER(ConvOp), C.c_int, C.POINTER(C.c_void_p)]),
+    'aivc_plan_graph_launch': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'aivc_plan_graph_destroy': (C.c_int, [C.c_void_p]),
     'aivc_nchw_to_fmap': (C.c_int, [C.c_void_p, C.POINTER(FMap), C.c_void_p]),
     'aivc_fmap_to_nchw': (C.c_int, [C.POINTER(FMap), C.c_void_p, C.c_void_p]),
     'aivc_fill_border': (C.c_int, [C.POINTER(FMap), C.c_void_p]),
@@ -112,6 +115,17 @@ def lib():
             raise RuntimeError('aivc_b200: ABI version mismatch')
         _lib = L
     return _lib
+
+
+PROFILING = False
+
+
+def set_profiling(on):
+    """Per-stage CUDA-event timing (aivc_profile_enable).  While it is on, plans run stage by stage instead of as
+    CUDA graphs."""
+    global PROFILING
+    PROFILING = bool(on)
+    lib().aivc_profile_enable(1 if on else 0)
 
 
 def check(rc):

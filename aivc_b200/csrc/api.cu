@@ -204,9 +204,10 @@ static int lanes_for_stream(cudaStream_t main_s, Lanes **out) {
     return 0;
 }
 
-int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
-    cudaStream_t main_s = (cudaStream_t)stream;
-    Lanes *l = nullptr;
+// `given`: side lane to use (graph capture brings its own, short-lived one); NULL: the caller stream's lane
+static int fused_seq(const aivc_conv_op *ops, int n, cudaStream_t main_s, Lanes *given) {
+    void *stream = (void *)main_s;
+    Lanes *l = given;
     bool side_dirty = false;
     for (int i = 0; i < n; ++i) {
         const int flags = g_prof_on ? 0 : ops[i].flags;   // per-stage timing needs kernels one at a time
@@ -232,6 +233,52 @@ int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
         AIVC_CHECK_CUDA(cudaEventRecord(l->join, l->side));
         AIVC_CHECK_CUDA(cudaStreamWaitEvent(main_s, l->join, 0));
     }
+    return 0;
+}
+
+int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream) {
+    return fused_seq(ops, n, (cudaStream_t)stream, nullptr);
+}
+
+// ---- a transform as ONE CUDA graph: the n kernel launches (with their programmatic-dependent-launch edges and the
+// fork / join of the two-lane attention branches) are captured once; replaying them costs one cudaGraphLaunch instead
+// of n launches and 3 n tensor-map encodes on the host, and the device schedules the nodes without host gaps.
+int aivc_plan_graph_create(const aivc_conv_op *ops, int n, void **graph_exec) {
+    if (!ops || n <= 0 || !graph_exec) AIVC_FAIL("plan_graph_create: bad arguments");
+    if (g_prof_on) AIVC_FAIL("plan_graph_create: per-stage profiling is on (stages are timed one by one, not as a graph)");
+    *graph_exec = nullptr;
+    cudaStream_t cs = nullptr;
+    Lanes tmp;
+    AIVC_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    AIVC_CHECK_CUDA(cudaStreamCreateWithFlags(&tmp.side, cudaStreamNonBlocking));
+    AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&tmp.fork, cudaEventDisableTiming));
+    AIVC_CHECK_CUDA(cudaEventCreateWithFlags(&tmp.join, cudaEventDisableTiming));
+    int rc = 0;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rc = fused_seq(ops, n, cs, &tmp);
+        e = cudaStreamEndCapture(cs, &g);                       // (also ends a capture that failed half way)
+    }
+    if (e == cudaSuccess && rc == 0) e = cudaGraphInstantiate(&ex, g, 0);
+    if (g) cudaGraphDestroy(g);
+    cudaEventDestroy(tmp.fork); cudaEventDestroy(tmp.join);
+    cudaStreamDestroy(tmp.side); cudaStreamDestroy(cs);
+    if (rc) return 1;                                           // (message set by the failing stage)
+    if (e != cudaSuccess) { cudaGetLastError(); AIVC_FAIL("plan_graph_create: %s", cudaGetErrorString(e)); }
+    *graph_exec = (void *)ex;
+    return 0;
+}
+
+int aivc_plan_graph_launch(void *graph_exec, void *stream) {
+    if (!graph_exec) AIVC_FAIL("plan_graph_launch: null graph");
+    AIVC_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return 0;
+}
+
+int aivc_plan_graph_destroy(void *graph_exec) {
+    if (graph_exec) AIVC_CHECK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
     return 0;
 }
 

@@ -44,13 +44,17 @@ class Config:
                                    # 'auto' = same as `precision`
     two_lanes: bool = True         # independent branches of attention blocks on two CUDA streams
     s2d_first: bool = True         # tensor-core engines: 5x5 stride-2 pixel-domain first layer as space-to-depth + 3x3 conv
+    cuda_graphs: bool = False      # replay every transform as one CUDA graph (plan.Plan.run).  Measured on B200: no gain
+                                   # (24.4 / 60.1 frames/s either way: the device is kernel-bound, the host keeps the
+                                   # queue full), so plain launches stay the default
     frames_in_flight: int = 1      # GOP coding: independent frames of a dependency level on this many streams
                                    # (codec.py::_lanes).  Measured on B200 (tools/lanes_ab.py): 2 lanes give +1 % (bf16x3)
                                    # / +2 % (bf16) for twice the buffers -- the device is already 95 % busy and
                                    # power-capped with one frame in flight -- so one lane is the default
 
     def key(self):
-        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first, self.frames_in_flight)
+        return (self.precision, self.tc_min_cin, self.hyper, self.two_lanes, self.s2d_first, self.frames_in_flight,
+                self.cuda_graphs)
 
     @property
     def tc(self):
@@ -64,7 +68,7 @@ class Config:
     def hyper_cfg(self):
         h = self.precision if self.hyper == 'auto' else self.hyper
         return Config(precision=h, tc_min_cin=self.tc_min_cin, hyper=h, two_lanes=self.two_lanes,
-                      s2d_first=self.s2d_first, frames_in_flight=self.frames_in_flight)
+                      s2d_first=self.s2d_first, frames_in_flight=self.frames_in_flight, cuda_graphs=self.cuda_graphs)
 
 
 DEFAULT = Config()
@@ -295,6 +299,7 @@ class Plan:
         pad_cout: round the last stage's output channels up to this multiple (extra channels
         get zero weights), so narrow pixel-domain outputs still fill a tensor-core tile."""
         self.cfg, self.device = cfg, torch.device(device)
+        self._graphs, self._warm = {}, set()
         g = Graph()
         self.src = T(h, w, cin, external=True)
         self.dst = lower(module, self.src, g)
@@ -520,8 +525,32 @@ class Plan:
         return fm
 
     def run(self):
+        """Enqueue the transform on the current stream.  With cfg.cuda_graphs the stages are replayed as ONE CUDA graph
+        (captured on the second call, after a plain first run has set the kernels' one-time attributes); a graph is
+        keyed by the pointers a caller may swap between runs (the last stage's out_scale = the per-frame-type gain)."""
         L = _lib.lib()
-        _lib.check(L.aivc_conv2d_fused_seq(self.ops, len(self.ops), _lib.stream_ptr()))
+        if not self.cfg.cuda_graphs or _lib.PROFILING:
+            _lib.check(L.aivc_conv2d_fused_seq(self.ops, len(self.ops), _lib.stream_ptr()))
+            return
+        key = self.ops[len(self.ops) - 1].out_scale
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._warm:
+                self._warm.add(key)
+                _lib.check(L.aivc_conv2d_fused_seq(self.ops, len(self.ops), _lib.stream_ptr()))
+                return
+            ex = C.c_void_p()
+            _lib.check(L.aivc_plan_graph_create(self.ops, len(self.ops), C.byref(ex)))
+            g = self._graphs[key] = ex
+        _lib.check(L.aivc_plan_graph_launch(g, _lib.stream_ptr()))
+
+    def __del__(self):
+        try:
+            L = _lib.lib()
+            for g in getattr(self, '_graphs', {}).values():
+                L.aivc_plan_graph_destroy(g)
+        except Exception:
+            pass
 
     def flops(self):
         """Algorithmic FLOPs of the reference graph: convs, tconvs and GDN 1x1."""

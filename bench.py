@@ -310,7 +310,7 @@ class Arm:
         self.barrier()
         l0 = L.aivc_launch_count()
         if profile:
-            L.aivc_profile_enable(1)
+            self._lib.set_profiling(True)
         # per-stage timing needs kernels one at a time: no second stream next to the timed stages
         # (the library likewise drops its two-lane execution while profiling)
         overlap = codec.mof.overlap_shortcut
@@ -335,7 +335,7 @@ class Arm:
             prof = list(out) + list(cls)
             if self.args.stage_csv and self.rank == 0 and getattr(self, 'dump_csv', True):
                 self._lib.check(L.aivc_profile_dump(self.args.stage_csv.encode()))
-            L.aivc_profile_enable(0)
+            self._lib.set_profiling(False)
         codec.mof.overlap_shortcut = codec.codec.overlap_shortcut = overlap
         codec.lanes_enabled = True
         launches = L.aivc_launch_count() - l0

@@ -155,6 +155,15 @@ int aivc_pack_conv_weight(const float *src, void *dst, int kind, int k, int cin,
 size_t aivc_packed_weight_bytes(int k, int engine, int cin_pad, int cout_pad);
 
 int aivc_conv2d_fused(const aivc_conv_op *op, void *stream);
+/* A transform as ONE CUDA graph: aivc_plan_graph_create captures the n stages exactly as aivc_conv2d_fused_seq would
+ * enqueue them (programmatic dependent launches, fork / join of the two-lane attention branches) on an internal stream
+ * -- nothing executes -- and instantiates the graph; aivc_plan_graph_launch replays it on `stream` (one launch call,
+ * no tensor-map encodes, no host gaps between the kernels).  The ops' pointers are baked in: re-create the graph when
+ * a buffer or parameter pointer changes.  Run the stages once through aivc_conv2d_fused_seq before capturing (one-time
+ * function attributes are set on first use).  Kernel launches inside a graph are not counted by aivc_launch_count. */
+int aivc_plan_graph_create(const aivc_conv_op *ops, int n, void **graph_exec);
+int aivc_plan_graph_launch(void *graph_exec, void *stream);
+int aivc_plan_graph_destroy(void *graph_exec);
 /* run n stages back to back on one stream (one FFI crossing per transform) */
 int aivc_conv2d_fused_seq(const aivc_conv_op *ops, int n, void *stream);
 

@@ -254,3 +254,30 @@ def test_two_frames_in_flight_same_bitstream(precision, dev):
             for x, y, z in zip(r1[f], r2[f], d2[f]):
                 assert torch.equal(x, y) and torch.equal(x, z), (rep, f)
     assert len(two._lanes()) == 2 and len(one._lanes()) == 1
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_cuda_graph_replay_same_bitstream(precision, dev):
+    """Config.cuda_graphs: every transform captured once (programmatic-dependent-launch edges, two-lane forks / joins
+    of the attention blocks) and replayed with one cudaGraphLaunch.  Same kernels, same order: bytes and planes equal
+    the plain-launch codec's over repeated GOPs, including the frame-type dependent gain pointer of g_a."""
+    from aivc_b200 import models, gop as G
+    from aivc_b200.codec import FrameCodec
+    from aivc_b200.plan import Config
+    h, w = 80, 112
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    gop = G.generate_gop_struct('1_GOP_4')
+    a, b = _noise_gops(2, h, w, 23, dev)
+    frames = [dict(a, frame_3=b['frame_0'], frame_4=b['frame_1']), dict(b, frame_3=a['frame_2'], frame_4=a['frame_0'])]
+    plain = FrameCodec(net, h, w, dev, Config(precision=precision, cuda_graphs=False))
+    graph = FrameCodec(net, h, w, dev, Config(precision=precision, cuda_graphs=True))
+    for rep in range(3):                        # rep 0: warm-up runs, rep 1: capture, rep 2: replay
+        for fr in frames:
+            b1, r1 = plain.encode_gop(fr, gop)
+            b2, r2 = graph.encode_gop(fr, gop)
+            d2 = graph.decode_gop(b2, gop)
+            assert b1 == b2, rep
+            for f in gop:
+                for x, y, z in zip(r1[f], r2[f], d2[f]):
+                    assert torch.equal(x, y) and torch.equal(x, z), (rep, f)
+    assert any(p._graphs for p in (graph.codec.g_a, graph.codec.g_s, graph.mof.g_a))
