@@ -308,7 +308,7 @@ class FrameCodec:
                                                   _lib.stream_ptr()))
 
     def _pack16(self, code, prev, nxt, into_codec):
-        """bf16 engine, uint8 planes: [code | prev | next] -> mof_in (and code -> codec_in) in ONE launch.
+        """tensor-core engines, uint8 planes: [code | prev | next] -> mof_in (and code -> codec_in) in ONE launch.
         None = the all-zero frame."""
         ptrs = []
         for planes in (code, prev, nxt):

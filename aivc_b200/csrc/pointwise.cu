@@ -105,7 +105,7 @@ __global__ void yuv420_to_fmap_kernel(const void *__restrict__ yp, const void *_
 }
 
 
-// Fused InputLayer for the bf16 engine: up to three 4:2:0 frames (code, prev, next; uint8 levels, a null
+// Fused InputLayer for the tensor-core engines (bf16 / split-bf16 buffers): up to three 4:2:0 frames (code, prev, next; uint8 levels, a null
 // luma pointer = the all-zero frame) -> channels 0..8 of the 16-channel level-unit pixel buffer, border
 // replicas included, channels 9..15 zero: ONE 32-byte store per pixel instead of three launches writing 6
 // bytes each.  `dst2` (optional) receives frame 0 alone in channels 0..2 (CodecNet input; its channels
@@ -186,7 +186,7 @@ __global__ void warp_blend_kernel(FMap mof, FMap prev, FMap next, int frame_is_p
                                   FMap skip, int levels, float *__restrict__ aux) {
     const int h = pred.h, w = pred.w;
     const size_t n = (size_t)h * w;
-    // both references are channel slices 3..5 / 6..8 of ONE 16-channel bf16 pixel buffer (the bf16 engine's mof_in)
+    // both references are channel slices 3..5 / 6..8 of ONE 16-channel bf16 pixel buffer (the tensor-core engines' mof_in)
     const bool x2 = prev.dtype == AIVC_BF16X2;                 // split-bf16 pixel: 16 hi + 16 lo elements
     const bool fast = (prev.dtype == AIVC_BF16 || x2) && next.dtype == prev.dtype && prev.data == next.data &&
                       prev.c_stride == (x2 ? 32 : 16) && prev.c_off == 3 && next.c_off == 6 && prev.pad == next.pad &&

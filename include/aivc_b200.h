@@ -181,7 +181,7 @@ int aivc_fmap_copy(const aivc_fmap *src, const aivc_fmap *dst, void *stream);
 int aivc_yuv420_to_fmap(const void *y, const void *u, const void *v, int u8, int levels,
                         const aivc_fmap *dst, void *stream);
 
-/* The same for the bf16 engine's 16-channel level-unit pixel buffers, fused: up to three uint8 4:2:0 frames
+/* The same for the tensor-core engines' 16-channel level-unit pixel buffers (bf16, or split bf16 with zero lo halves), fused: up to three uint8 4:2:0 frames
  * (frame to code, previous and next reference; a NULL luma pointer = the all-zero frame, decode.py:710-714)
  * -> channels 0..8 of `dst` (whole pixel, border replicas included, channels 9..15 zero) in one launch;
  * `dst2` (optional) receives frame 0 alone in channels 0..2 (CodecNet input [code | pred]). */
