@@ -9,6 +9,7 @@
                an LDP_8 GOP in coding order), stand-in seed 4, C=128
   ra1080     : configs[2] -- synthetic 1920x1080, random access I, P, B ('1_GOP_2': every frame type of 1_GOP_32),
                stand-in seed 1234 (the benchmark model), C=128
+  ra1080_gop8: the same model on a 9-frame random-access GOP ('1_GOP_8': B frames three levels deep)
 
 Per frame the fixture keeps: the quantised latent indices of both nets (int8/int16, what north_star asks to be
 bit-exact), the z indices, length + md5 of the frame's bitstream bytes, md5 of the reconstructed planes, a 1/16
@@ -33,6 +34,9 @@ CASES = {
     'bubbles240': dict(h=240, w=416, gop='1_GOP_0', model=dict(seed=7, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)), src='bubbles'),
     'ldp720': dict(h=720, w=1280, gop='LDP_2', model=dict(seed=4, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)), src=('synth', 720)),
     'ra1080': dict(h=1080, w=1920, gop='1_GOP_2', model=dict(seed=1234, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)), src=('synth', 1080)),
+    # a deeper random-access hierarchy (9 frames, dependency levels of 1, 1, 1, 2, 4 frames): does the distance to the
+    # oracle grow along the reference chain?
+    'ra1080_gop8': dict(h=1080, w=1920, gop='1_GOP_8', model=dict(seed=1234, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)), src=('synth', 1081)),
 }
 
 

@@ -12,7 +12,9 @@ MODELS = {
     'bubbles240': dict(seed=7, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)),
     'ldp720': dict(seed=4, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)),
     'ra1080': dict(seed=1234, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)),
+    'ra1080_gop8': dict(seed=1234, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0)),
 }
+SYNTH_SEED = {'ldp720': 720, 'ra1080': 1080, 'ra1080_gop8': 1081}
 
 
 def source_frames(case, fx):
@@ -21,7 +23,8 @@ def source_frames(case, fx):
     if case == 'bubbles240':
         d = np.load(os.path.join(GOLDEN, 'bubbles_416x240_frame0.npz'))
         return [(d['y'], d['u'], d['v'])]
-    return synth.clip(h, 3, h, w)
+    n = sum(1 for k in fx.files if k.endswith('_type'))
+    return synth.clip(SYNTH_SEED[case], n, h, w)
 
 
 def psnr(a, b):

@@ -11,7 +11,7 @@ from tests import parity_cfg       # noqa: E402
 
 dev = torch.device('cuda:0')
 res = []
-for case in ('bubbles240', 'ldp720', 'ra1080'):
+for case in ('bubbles240', 'ldp720', 'ra1080', 'ra1080_gop8'):
     for prec in ('fp32', 'bf16x3', 'bf16'):
         r = parity_cfg.measure(case, prec, dev)
         res.append(r)
@@ -20,4 +20,7 @@ for case in ('bubbles240', 'ldp720', 'ra1080'):
               % (r['y_mismatches'], r['y_symbols'], r['y_max_abs_diff'], r['z_mismatches'], r['z_symbols'], r['bytes'],
                  r['oracle_bytes'], r['frames_bytes_identical'], r['n_frames'], r['frames_planes_identical'], r['n_frames'],
                  r['max_level_diff_subsampled'], r['max_abs_psnr_delta_db'], r['closed_loop_exact']), flush=True)
+        if case == 'ra1080_gop8':        # along the reference chain, in coding order
+            print('    per frame (coding order) y mismatches mof/codec:',
+                  [(f, fr.get('mof', {}).get('y_mismatches'), fr['codec']['y_mismatches']) for f, fr in r['frames'].items()], flush=True)
 json.dump(res, open(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/r02_parity_configs.json', 'w'), indent=1)
