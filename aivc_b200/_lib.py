@@ -34,7 +34,7 @@ class ConvOp(C.Structure):
                 ('alg_flops', C.c_double)]
 
 
-OP_LANE1, OP_FORK, OP_JOIN = 1, 2, 4
+OP_LANE1, OP_FORK, OP_JOIN, OP_IN_EXACT = 1, 2, 4, 8
 KERNEL_CLASSES = ('conv_simt_kernel', 'conv_tc_kernel', 'conv3x3_tc_kernel', 'conv3x3_tc_gdn_kernel',
                   'conv1x1_tc_kernel', 'col2im_tconv_kernel', 'space_to_depth_kernel', 'tconv3x3_tc_kernel')
 

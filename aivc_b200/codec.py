@@ -60,7 +60,8 @@ def _gain_vec(gm, idx_rate, mode, c):
 class CondNetEngine:
     """Kernel plans and staging buffers of one ConditionalNet at a fixed frame size."""
 
-    def __init__(self, net, h, w, in_buf, in_c, ref_off, ref_c, device, cfg, idx_rate=0., levels=False):
+    def __init__(self, net, h, w, in_buf, in_c, ref_off, ref_c, device, cfg, idx_rate=0., levels=False,
+                 in_exact=False):
         self.net, self.device = net, device
         cy, cz, csc = net.nb_ft_y, net.nb_ft_z, net.out_c_shortcut_y
         self.cy, self.cz, self.csc = cy, cz, csc
@@ -75,7 +76,7 @@ class CondNetEngine:
         self.h_s = Plan(net.h_s, hz, wz, cz, device, exact)
         if getattr(net, 'g_a', None) is not None:        # a decoder-only model has no analysis side
             self.g_a = Plan(net.g_a, h, w, in_c, device, cfg, src_buf=in_buf,
-                            out_scale=torch.ones(cy), in_embed=embed(0))
+                            out_scale=torch.ones(cy), in_embed=embed(0), in_exact=in_exact)
             # y stays fp32 for the quantiser; a tensor-core h_a reads a bf16, bordered copy of it
             self.h_a = Plan(net.h_a, hy, wy, cy, device, exact,
                             src_buf=self.g_a.dst.buf if exact.precision == 'fp32' else None,
@@ -84,7 +85,7 @@ class CondNetEngine:
         if self.has_ref:
             self.g_a_ref = Plan(net.g_a_ref, h, w, ref_c, device, cfg, src_buf=in_buf,
                                 src_c_off=0 if tc else ref_off, dst_into=(self.gs_in, cy),
-                                in_embed=embed(ref_off))
+                                in_embed=embed(ref_off), in_exact=in_exact)
         self.table = entropy.z_table_u16(net.pdf_z)
         self.gains = {}
         for ft in (FRAME_I, FRAME_P, FRAME_B):
@@ -284,8 +285,9 @@ class FrameCodec:
                 self.mof_in = Buffer(h, w, 9, 0, F32, self.device)
                 self.codec_in = Buffer(h, w, 6, 0, F32, self.device)
             self.skip = Buffer(h, w, 3, 0, F32, self.device)
+            # (MOFNet reads code | prev | next: 8-bit levels, exact in bf16 when the frames arrive as uint8 planes)
             self.mof = CondNetEngine(model.mode_net.mode_net, h, w, self.mof_in, 9, 3, 6, self.device,
-                                     self.cfg, idx_rate, self.levels)
+                                     self.cfg, idx_rate, self.levels, in_exact=self.levels)
             self.codec = CondNetEngine(model.codec_net.codec_net, h, w, self.codec_in, 6, 3, 3,
                                        self.device, self.cfg, idx_rate, self.levels)
             hc, wc = (h + 1) // 2, (w + 1) // 2
@@ -302,6 +304,10 @@ class FrameCodec:
     def _pack(self, planes, buf, c_off):
         y, u, v = planes
         u8 = 1 if y.dtype == torch.uint8 else 0
+        if not u8 and buf is self.mof_in and self.levels:      # float planes need not be 8-bit levels: full split product
+            for pl in (getattr(self.mof, 'g_a', None), getattr(self.mof, 'g_a_ref', None)):
+                if pl is not None:
+                    pl.set_input_exact(False)
         fm = buf.view(c_off, 3)
         _lib.check(_lib.lib().aivc_yuv420_to_fmap(y.data_ptr(), u.data_ptr(), v.data_ptr(), u8,
                                                   1 if self.levels else 0, C.byref(fm),

@@ -210,7 +210,7 @@ static int fused_seq(const aivc_conv_op *ops, int n, cudaStream_t main_s, Lanes 
     Lanes *l = given;
     bool side_dirty = false;
     for (int i = 0; i < n; ++i) {
-        const int flags = g_prof_on ? 0 : ops[i].flags;   // per-stage timing needs kernels one at a time
+        const int flags = g_prof_on ? 0 : (ops[i].flags & (AIVC_OP_LANE1 | AIVC_OP_FORK | AIVC_OP_JOIN));   // per-stage timing needs kernels one at a time
         if (flags && !l && lanes_for_stream(main_s, &l)) return 1;
         if (flags & AIVC_OP_FORK) {
             AIVC_CHECK_CUDA(cudaEventRecord(l->fork, main_s));

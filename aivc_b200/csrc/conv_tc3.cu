@@ -63,6 +63,7 @@ struct Tc3Params {
     uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
     int tma_store;                    // epilogue stores through smem + TMA (bf16, 32-channel multiples)
+    int skip_lo;                      // split-bf16 input with all-zero lo halves (AIVC_OP_IN_EXACT): no lo.Whi part
     int x3, kv, a_lo, b_lo;           // split-bf16 operands (AIVC_ENGINE_TC_X3): kv = 3 * kchunks virtual chunks
                                       // (hi.Whi, lo.Whi, hi.Wlo); channel coordinates of the lo halves
 };
@@ -71,7 +72,9 @@ struct Tc3Params {
 __device__ __forceinline__ void chunk_coords(const Tc3Params &p, int kc, int &ca, int &cb) {
     ca = cb = kc * 64;
     if (p.x3) {
-        const int part = kc / p.kchunks, j = kc - part * p.kchunks;
+        int part = kc / p.kchunks;
+        const int j = kc - part * p.kchunks;
+        if (p.skip_lo && part == 1) part = 2;                   // (two parts only: hi.Whi, hi.Wlo)
         ca = j * 64 + (part == 1 ? p.a_lo : 0);
         cb = j * 64 + (part == 2 ? p.b_lo : 0);
     }
@@ -1004,8 +1007,9 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int tiles32 = tiles_x * ceil_div(op->out.h, 32);
     int sub = tiles32 >= 296 ? 2 : 1;
     if (gdn) sub = 1;                                          // conv + GDN kernel: 16-row tiles, one CTA per SM
-    else if (tiles32 >= 148 && tiles32 < 296) return -1;       // one-and-a-bit waves of 32-row tiles: the generic
-                                                               // 128-pixel-tile kernel fills the chip better (measured)
+    else if (tiles32 >= 148 && tiles32 < 296 && !x3) return -1;     // one-and-a-bit waves of 32-row tiles: the generic
+                                                               // 128-pixel-tile kernel fills the chip better (measured,
+                                                               // plain bf16; split bf16: 16-row tiles, see below)
     const int tile_h = 16 * sub;
     const int ntiles = tiles_x * ceil_div(op->out.h, tile_h);
 
@@ -1016,7 +1020,8 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     if (op->gate.data) p.gate = to_dev(op->gate);
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / 64;
-    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? 3 : 1) * p.kchunks; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
+    p.skip_lo = (x3 && (op->flags & AIVC_OP_IN_EXACT)) ? 1 : 0;
+    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? (p.skip_lo ? 2 : 3) : 1) * p.kchunks; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
     // small layers (SUB = 1): output channels split over two work items, two CTAs per SM, shallow weight ring
     p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
     p.ncta = cout / p.nsplit;

@@ -292,14 +292,16 @@ class Plan:
 
     def __init__(self, module, h, w, cin, device, cfg=DEFAULT, src_buf=None, src_c_off=0,
                  dst_into=None, out_scale=None, out_post='none', in_dtype=None, in_embed=None,
-                 pad_cout=0, out_dtype=None, out_pad=0):
+                 pad_cout=0, out_dtype=None, out_pad=0, in_exact=False):
         """in_embed=(buffer_channels, offset, weight_scale): the module's `cin` input channels
         are channels [offset, offset+cin) of a wider (zero-padded) pixel of `buffer_channels`
         channels; the first stage's weights are embedded accordingly and scaled.
         pad_cout: round the last stage's output channels up to this multiple (extra channels
-        get zero weights), so narrow pixel-domain outputs still fill a tensor-core tile."""
+        get zero weights), so narrow pixel-domain outputs still fill a tensor-core tile.
+        in_exact: every input channel holds values that are exact in bf16 (8-bit level units): in the split-bf16 mode
+        the stages reading the input (through the space-to-depth repack) skip the lo.Whi third of their MMAs."""
         self.cfg, self.device = cfg, torch.device(device)
-        self._graphs, self._warm = {}, set()
+        self._graphs, self._warm, self._in_exact = {}, set(), True
         g = Graph()
         self.src = T(h, w, cin, external=True)
         self.dst = lower(module, self.src, g)
@@ -316,6 +318,11 @@ class Plan:
             self._split_narrow_tconvs()
             if in_embed is not None and cfg.s2d_first:
                 self._space_to_depth_first_layer()
+            if in_exact and cfg.precision == 'bf16x3':
+                first = {id(s.dst) for s in self.stages if s.kind == 3 and s.src is self.src}
+                for s in self.stages:
+                    if s.kind == 0 and (s.src is self.src or id(s.src) in first):
+                        s.flags |= _lib.OP_IN_EXACT
         last = self.stages[-1]
         self.out_c = self.dst.c
         if pad_cout and self.dst.c % pad_cout and last.kind != 2:
@@ -461,7 +468,7 @@ class Plan:
             op = self.ops[i]
             cin, cout = s.src.c, s.dst.c
             op.kind, op.k, op.stride, op.engine = s.kind, s.k, s.stride, s.engine
-            op.flags = s.flags if self.cfg.two_lanes else 0
+            op.flags = s.flags if self.cfg.two_lanes else (s.flags & _lib.OP_IN_EXACT)
             op.inp, op.out = s.src.fmap(), s.dst.fmap()
             op.alg_flops = s.alg_flops
             if s.kind == 3:
@@ -532,7 +539,7 @@ class Plan:
         if not self.cfg.cuda_graphs or _lib.PROFILING:
             _lib.check(L.aivc_conv2d_fused_seq(self.ops, len(self.ops), _lib.stream_ptr()))
             return
-        key = self.ops[len(self.ops) - 1].out_scale
+        key = (self.ops[len(self.ops) - 1].out_scale, self._in_exact)
         g = self._graphs.get(key)
         if g is None:
             if key not in self._warm:
@@ -543,6 +550,16 @@ class Plan:
             _lib.check(L.aivc_plan_graph_create(self.ops, len(self.ops), C.byref(ex)))
             g = self._graphs[key] = ex
         _lib.check(L.aivc_plan_graph_launch(g, _lib.stream_ptr()))
+
+    def set_input_exact(self, exact):
+        """Stages flagged OP_IN_EXACT (see `in_exact`) skip the lo halves of their input only while the caller vouches
+        that the input is exact in bf16 (uint8 planes); float planes switch the full three-part product back on."""
+        exact = bool(exact)
+        if exact != self._in_exact:
+            for op, s in zip(self.ops, self.stages):
+                if s.flags & _lib.OP_IN_EXACT:
+                    op.flags = (op.flags | _lib.OP_IN_EXACT) if exact else (op.flags & ~_lib.OP_IN_EXACT)
+            self._in_exact = exact
 
     def __del__(self):
         try:

@@ -113,7 +113,9 @@ typedef struct {
 enum {
     AIVC_OP_LANE1 = 1,   /* run this stage on the side stream */
     AIVC_OP_FORK = 2,    /* before it: side stream waits for everything queued on the caller's stream */
-    AIVC_OP_JOIN = 4     /* before it: caller's stream waits for everything queued on the side stream */
+    AIVC_OP_JOIN = 4,    /* before it: caller's stream waits for everything queued on the side stream */
+    AIVC_OP_IN_EXACT = 8 /* split-bf16 input whose lo halves are all zero (8-bit level units straight from the pixel
+                          * buffers): the lo.Whi third of the MMAs is skipped (persistent 3x3 kernels) */
 };
 
 /* ---- library ----------------------------------------------------------------------- */

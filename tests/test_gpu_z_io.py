@@ -281,3 +281,35 @@ def test_cuda_graph_replay_same_bitstream(precision, dev):
                 for x, y, z in zip(r1[f], r2[f], d2[f]):
                     assert torch.equal(x, y) and torch.equal(x, z), (rep, f)
     assert any(p._graphs for p in (graph.codec.g_a, graph.codec.g_s, graph.mof.g_a))
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16', 'fp32'])
+def test_float_planes_and_uint8_planes_agree(precision, dev):
+    """encode_gop takes uint8 planes or fp32 planes in [0, 1].  Float planes holding 8-bit levels (what the reference
+    feeds: PNG-sourced frames / 255) give the same bytes as the uint8 planes -- in the split-bf16 mode the stages that
+    skip the lo halves of an exact input switch to the full product for float planes --, and float planes that are NOT
+    8-bit levels still round-trip (decoder == encoder)."""
+    from aivc_b200 import models, gop as G
+    from aivc_b200.codec import FrameCodec
+    from aivc_b200.plan import Config
+    h, w = 80, 112
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    gop = G.generate_gop_struct('1_GOP_2')
+    u8 = _noise_gops(1, h, w, 31, dev)[0]
+    as_float = {f: tuple(p.float() / 255. for p in u8[f]) for f in u8}
+    codec = FrameCodec(net, h, w, dev, Config(precision=precision))
+    b_u8, r_u8 = codec.encode_gop(u8, gop)
+    b_f, r_f = codec.encode_gop(as_float, gop)
+    assert b_f == b_u8
+    for f in gop:
+        for x, y in zip(r_u8[f], r_f[f]):
+            assert torch.equal(x, y)
+    g = torch.Generator(device='cpu').manual_seed(1)
+    odd = {f: tuple(torch.rand(p.shape, generator=g).to(dev) for p in u8[f]) for f in u8}     # not 8-bit levels
+    b_o, r_o = codec.encode_gop(odd, gop)
+    d_o = codec.decode_gop(b_o, gop)
+    for f in gop:
+        for x, y in zip(r_o[f], d_o[f]):
+            assert torch.equal(x, y)
+    b_again, _ = codec.encode_gop(u8, gop)                    # and back to uint8 planes: unchanged bytes
+    assert b_again == b_u8
