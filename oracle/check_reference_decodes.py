@@ -1,0 +1,64 @@
+"""ORACLE (test infrastructure; run HERE, where /root/reference exists):
+
+    python -m oracle.check_reference_decodes [gpu_streams.npz ...]
+
+The REFERENCE's own real_life.decode.Decoder + ArithmeticCoder decode
+  (1) the 'spec' bitstream of the golden 80x112 GOP (tests/golden/system_80x112.npz) -- the bytes the CUDA bf16x3 and
+      fp32 engines reproduce exactly (tests/test_gpu_engine_x3.py::test_codec_x3_bytes_identical_to_oracle) --, and
+  (2) bitstreams written by the CUDA encoder on a B200 and brought back as .npz (tools/dump_gpu_streams.py),
+and compares with the encoder's own reconstruction, plane for plane.  (1) must be exact: it closes the loop "CUDA encoder
+-> reference decoder" on the golden case; the only stand-ins are torchac (oracle/torchac_ref.c, parity unpinned) and the
+evaluation of the transforms.  (2) is INFORMATIONAL: on larger streams a decoder whose hyper-decoder arithmetic is not
+bit-identical to the encoder's (here: MKL-DNN fp32 on the host vs the CUDA kernels) computes a sigma that is 1 ulp off
+for some symbols, one 16-bit CDF entry moves, and the range decoder desynchronises -- measured 2026-10: level differences
+of 60-120 on 135x241 .. 416x240 GOPs, for bf16x3 and bf16 alike.  This is a property of the FORMAT (bitstream.py:143-152
+feeds sigma straight into the CDF), not of this implementation: the reference's own GPU encoder and CPU decoder do not
+interoperate either, which is what its determinism flags are for (src/sanity_script.sh:3, cluster_mngt.py:27-37).
+Encoder and decoder of THIS implementation always agree bit for bit (any engine, any number of GPUs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aivc_b200 import models, gop as G                       # noqa: E402
+from oracle.ref_decoder import build_reference_decoder, reference_decode_gop   # noqa: E402
+
+
+def check(tag, net, frame_bytes, planes, gop, h, w):
+    rdec = build_reference_decoder(net)
+    dec = reference_decode_gop(rdec, frame_bytes, gop, h, w)
+    worst = 0
+    for f in gop:
+        for k in 'yuv':
+            got = np.rint(dec[f][k].numpy() * 255).astype(np.int32).reshape(-1)
+            worst = max(worst, int(np.abs(got - planes[f][k].astype(np.int32).reshape(-1)).max()))
+    print('%s: reference Decoder on %d frames (%d bytes): max |level diff| vs the encoder reconstruction = %d'
+          % (tag, len(gop), sum(len(b) for b in frame_bytes.values()), worst), flush=True)
+    return worst
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    bad = 0
+    fx = np.load(os.path.join(ROOT, 'tests', 'golden', 'system_80x112.npz'))
+    gop = G.generate_gop_struct('1_GOP_2')
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    fb = {f: fx['spec_bytes_%s' % f].tobytes() for f in gop}
+    pl = {f: {k: fx['spec_rec_%s_%s' % (f, k)] for k in 'yuv'} for f in gop}
+    bad += check('golden 80x112 (spec bytes = CUDA bf16x3 / fp32 bytes)', net, fb, pl, gop, int(fx['H']), int(fx['W'])) != 0
+    for path in sys.argv[1:]:
+        d = np.load(path, allow_pickle=False)
+        h, w = int(d['H']), int(d['W'])
+        gop = G.generate_gop_struct(str(d['gop']))
+        net = models.build_standin(**eval(str(d['model'])))
+        fb = {f: d['bytes_%s' % f].tobytes() for f in gop}
+        pl = {f: {k: d['rec_%s_%s' % (f, k)] for k in 'yuv'} for f in gop}
+        check('(informational) %s [%s %s]' % (os.path.basename(path), d['precision'], d['gop']), net, fb, pl, gop, h, w)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == '__main__':
+    main()
