@@ -49,6 +49,21 @@ def main():
     fb = {f: fx['spec_bytes_%s' % f].tobytes() for f in gop}
     pl = {f: {k: fx['spec_rec_%s_%s' % (f, k)] for k in 'yuv'} for f in gop}
     bad += check('golden 80x112 (spec bytes = CUDA bf16x3 / fp32 bytes)', net, fb, pl, gop, int(fx['H']), int(fx['W'])) != 0
+    # the integer-CDF recipe the CUDA path uses ('spec': csrc/laplace_cdf.h) is interchangeable with torch's float table:
+    # the oracle encoder in 'spec' mode, decoded by the reference's decoder (same host arithmetic for sigma), at 416x240
+    from oracle import codec_ref as O
+    from tests import synth
+    h, w = 240, 416
+    net = models.build_standin(seed=7, C=128, Cy=64, Cz=64, Csc=64, hyper_boost=(12.0, 8.0))
+    gop = G.generate_gop_struct('1_GOP_2')
+    names = sorted(gop, key=lambda f: int(f.split('_')[1]))
+    clip = synth.clip(6, len(names), h, w)
+    yuv = {f: {k: torch.from_numpy(p.astype(np.float32) / 255.)[None, None] for k, p in zip('yuv', clip[i])}
+           for i, f in enumerate(names)}
+    with torch.no_grad():
+        fb, rec = O.encode_gop(net, O.Tables(net), yuv, gop, cdf_mode='spec')
+    pl = {f: {k: np.rint(rec[f][k].numpy() * 255) for k in 'yuv'} for f in gop}
+    bad += check("oracle encoder, 'spec' integer CDFs, 416x240 C=128", net, fb, pl, gop, h, w) != 0
     for path in sys.argv[1:]:
         d = np.load(path, allow_pickle=False)
         h, w = int(d['H']), int(d['W'])
