@@ -313,3 +313,27 @@ def test_float_planes_and_uint8_planes_agree(precision, dev):
             assert torch.equal(x, y)
     b_again, _ = codec.encode_gop(u8, gop)                    # and back to uint8 planes: unchanged bytes
     assert b_again == b_u8
+
+
+def test_closed_loop_2160p(dev):
+    """Maximum size of practical interest (3840x2160, four times the benchmark's pixels): tensor-map extents, buffer
+    offsets beyond 2^31 bytes and the persistent kernels' tile counters at 4K; I, P and B frame, default engine,
+    small-width stand-in (the geometry is what is being tested)."""
+    from aivc_b200 import models, gop as G
+    from aivc_b200.codec import FrameCodec
+    from aivc_b200.plan import Config
+    h, w = 2160, 3840
+    net = models.build_standin(seed=5, C=64, Cy=32, Cz=32, Csc=32)
+    gop = G.generate_gop_struct('1_GOP_2')
+    g = torch.Generator(device='cpu').manual_seed(4)
+    frames = {f: tuple(torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).to(dev)
+                       for n in (h * w, h * w // 4, h * w // 4)) for f in gop}
+    codec = FrameCodec(net, h, w, dev, Config())
+    bts, rec = codec.encode_gop(frames, gop)
+    dec = codec.decode_gop(bts, gop)
+    for f in gop:
+        assert len(bts[f]) > 1000
+        for a, b in zip(rec[f], dec[f]):
+            assert torch.equal(a, b), f
+    del codec
+    torch.cuda.empty_cache()
