@@ -76,3 +76,26 @@ def test_metrics_oracle_reproduces_reference_golden(golden_dir):
         a, b = Gm.planes(int(seed), int(h), int(w))
         got = M.frame_metrics(Gm.as_dic(a), Gm.as_dic(b))
         assert abs(got['mse'] - mse) <= 1e-9 and abs(got['ms_ssim'] - ms) <= 2e-6
+
+
+def test_reference_decoder_reads_the_cuda_encoders_golden_bitstream():
+    """The REFERENCE's own real_life.decode.Decoder + ArithmeticCoder (torchac shimmed, transforms evaluated by the
+    oracle) decode the golden GOP's 'spec' bitstream -- byte for byte what the CUDA bf16x3 and fp32 encoders write
+    (tests/test_gpu_engine_x3.py::test_codec_x3_bytes_identical_to_oracle, test_gpu_parity.py::
+    test_codec_fp32_bit_exact_vs_oracle) -- to exactly the encoder's reconstruction.  Needs the reference tree."""
+    import os
+    import numpy as np
+    import pytest
+    if not os.path.isdir('/root/reference/src'):
+        pytest.skip('reference tree not present')
+    from aivc_b200 import models, gop as G
+    from oracle.ref_decoder import build_reference_decoder, reference_decode_gop
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'system_80x112.npz'))
+    gop = G.generate_gop_struct('1_GOP_2')
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16)
+    dec = reference_decode_gop(build_reference_decoder(net), {f: fx['spec_bytes_%s' % f].tobytes() for f in gop}, gop,
+                               int(fx['H']), int(fx['W']))
+    for f in gop:
+        for k in 'yuv':
+            got = np.rint(dec[f][k].numpy() * 255).astype(np.uint8).reshape(-1)
+            assert np.array_equal(got, fx['spec_rec_%s_%s' % (f, k)].reshape(-1)), (f, k)
