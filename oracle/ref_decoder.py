@@ -15,24 +15,37 @@ import torch
 REF_SRC = '/root/reference/src'
 
 
+_PREFIXES = ('layers', 'models', 'real_life', 'func_util', 'model_mngt', 'torchac')
+
+
 def reference_modules():
-    """Import the reference's modules (torchac shimmed); returns a namespace dict."""
+    """Import the REFERENCE's modules (torchac shimmed) and return the classes needed, whatever is registered under
+    their names at the moment: aivc_b200.compat.install() aliases `layers.*` to the CUDA mirrors in sys.modules, and an
+    oracle must not pick those up.  sys.modules / sys.path are restored afterwards."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p in (root, REF_SRC):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    from oracle import torchac_shim
-    sys.modules['torchac'] = torchac_shim
-    ns = {}
-    with contextlib.redirect_stdout(io.StringIO()):
-        from layers.misc import misc_layers as rm
-        from layers.ae import ae_layers as rae
-        from layers.multi_rate.gain_matrix import GainMatrix as RefGain
-        from func_util.optical_flow import warp as ref_warp
-        from real_life.bitstream import ArithmeticCoder
-        from real_life.decode import Decoder as RefDecoder
-    ns.update(rm=rm, rae=rae, RefGain=RefGain, ref_warp=ref_warp, ArithmeticCoder=ArithmeticCoder, RefDecoder=RefDecoder)
-    return ns
+    saved = {k: v for k, v in sys.modules.items() if k.split('.')[0] in _PREFIXES}
+    for k in saved:
+        del sys.modules[k]
+    old_path = list(sys.path)
+    sys.path[:0] = [REF_SRC, root]
+    try:
+        from oracle import torchac_shim
+        sys.modules['torchac'] = torchac_shim
+        with contextlib.redirect_stdout(io.StringIO()):
+            from layers.misc import misc_layers as rm
+            from layers.ae import ae_layers as rae
+            from layers.multi_rate.gain_matrix import GainMatrix as RefGain
+            from func_util.optical_flow import warp as ref_warp
+            from real_life.bitstream import ArithmeticCoder
+            from real_life.decode import Decoder as RefDecoder
+        assert rm.__file__.startswith(REF_SRC), rm.__file__
+        return dict(rm=rm, rae=rae, RefGain=RefGain, ref_warp=ref_warp, ArithmeticCoder=ArithmeticCoder,
+                    RefDecoder=RefDecoder)
+    finally:
+        for k in [k for k in sys.modules if k.split('.')[0] in _PREFIXES]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = old_path
 
 
 def build_reference_decoder(net):
