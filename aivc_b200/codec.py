@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, entropy
-from ._lib import F32, BF16, BF16X2
+from ._lib import F32
 from .gop import FRAME_I, FRAME_P, FRAME_B, coding_order
 from .plan import Plan, Buffer, Config
 

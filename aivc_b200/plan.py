@@ -20,7 +20,7 @@ recycled by liveness.  All stages of a plan run with ONE ctypes call
 """
 import ctypes as C
 import weakref
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import torch
