@@ -56,7 +56,7 @@ template <int BK>
 __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmG,
-                                                           const TcParams p) {
+                                                           const __grid_constant__ TcParams p) {
     constexpr int ROWB = BK * 2;
     constexpr int IPS = 64 / BK;                // (tap, chunk) items per pipeline stage
     extern __shared__ uint8_t smem_raw[];
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
         }
 
         if (p.gdn) {
-            const bool interior = ctx.out.pad == 0 || (oy > 0 && oy < p.out.h - 1 && ox > 0 && ox < p.out.w - 1);
+            const bool interior = p.out.pad == 0 || (oy > 0 && oy < p.out.h - 1 && ox > 0 && ox < p.out.w - 1);
             const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
 #pragma unroll 1
             for (int j0 = 0; j0 < N; j0 += 16) {

@@ -146,7 +146,7 @@ __device__ __forceinline__ void epilogue(const Tc1Params &p, const CUtensorMap *
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmO, const Tc1Params p) {
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Tc1Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full[NS], empty[NS], acc_full[NS], acc_empty[NS], b_full;
     __shared__ uint32_t tmem_slot;

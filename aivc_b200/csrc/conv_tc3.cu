@@ -188,7 +188,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
         const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
         const bool valid = (oy < p.out.h) && (ox < p.out.w);
         const bool use_res = res_fast && valid;
-        ctx.out.c_off = p.out.c_off + n0;
+        ctx.ch0 = n0;                                             // (channels [n0, n0 + N) of out / res / gate)
         const __nv_bfloat16 *res_px = use_res ? (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0) : nullptr;
         uint4 rr[4];
         if (res_fast) {
@@ -225,7 +225,6 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
                     store_pending = true;
                 }
             } else {
-                ctx.res.c_off = p.res.c_off + n0; ctx.gate.c_off = p.gate.c_off + n0;
                 epi_row<ACT>(tl, c_hi, sbias + n0, sscale + n0, ctx, oy, ox, valid, c_lo);
             }
         }
@@ -238,7 +237,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
 template <int SUB, bool RES>
 __global__ void __launch_bounds__(Cfg<SUB>::NTHREADS, SUB == 1 ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
+                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Tc3Params p) {
     using K = Cfg<SUB>;
     constexpr int NTHREADS = K::NTHREADS, TILE_H = K::TILE_H;
     constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
@@ -406,7 +405,7 @@ template <bool RES>
 __global__ void __launch_bounds__(GDN_THREADS, 1)
 conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmG,
-                      const Tc3Params p, const float *gdn_beta, int inverse) {
+                      const __grid_constant__ Tc3Params p, const float *gdn_beta, int inverse) {
     using K = Cfg<1>;
     constexpr int NTHREADS = GDN_THREADS, TILE_H = K::TILE_H;
     constexpr uint32_t A_SLOT = K::A_SLOT, PATCH_BYTES = K::PATCH_BYTES;
@@ -830,7 +829,7 @@ __device__ __forceinline__ void tconv_epilogue(const Tc3Params &p, const CUtenso
 
 __global__ void __launch_bounds__(Cfg<2>::NTHREADS, 1)
 tconv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmO, const Tc3Params p) {
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Tc3Params p) {
     using K1 = Cfg<1>;
     constexpr int NTHREADS = Cfg<2>::NTHREADS, TMA_WARP = 16, MMA_WARP = 17;
     constexpr uint32_t A_SLOT = K1::A_SLOT, PATCH_BYTES = K1::PATCH_BYTES;

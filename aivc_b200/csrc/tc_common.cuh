@@ -265,8 +265,12 @@ __device__ __forceinline__ void store16(const FMap &m, bool vec, int y, int x, i
 // Everything that does not depend on the element (activation kind, presence of gate / residual /
 // scale, vector alignment, border replication) is decided once per row, outside the channel loop;
 // bias and scale are read from shared memory as broadcast float4.
+// The maps are referenced, not copied: they live in the kernel's __grid_constant__ parameter block (constant bank), so
+// an epilogue does not spend ~40 registers (or local-memory spills) on three FMap structs.  `ch0` is added to every
+// channel index of out / res / gate (a work item that covers output channels [ch0, ch0 + N) of the stage).
 struct EpiCtx {
-    FMap out, res, gate;
+    const FMap *outp, *resp, *gatep;
+    int ch0;
     int post, act_channels;
     bool has_scale, out_vec, res_vec, gate_vec;
     bool precise;       // bf16x3 mode: IEEE sigmoid / sqrt / division instead of the fast approximations
@@ -275,7 +279,7 @@ struct EpiCtx {
 __device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, const FMap &gate, int post,
                                            int act_channels, bool has_scale, bool precise = false) {
     EpiCtx c;
-    c.out = out; c.res = res; c.gate = gate; c.post = post; c.act_channels = act_channels;
+    c.outp = &out; c.resp = &res; c.gatep = &gate; c.ch0 = 0; c.post = post; c.act_channels = act_channels;
     c.has_scale = has_scale;
     c.precise = precise;
     c.out_vec = fmap_vec_ok(out);
@@ -366,24 +370,24 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
     if (gb) {                       // gate row prefetched as packed bf16 (split maps: [2..3] = the lo halves)
         float g[16];
         unpack_bf16x16(gb, g);
-        if (c.gate.dtype == AIVC_BF16X2) { add_packed_bf16x8(g, gb[2]); add_packed_bf16x8(g + 8, gb[3]); }
+        if (c.gatep->dtype == AIVC_BF16X2) { add_packed_bf16x8(g, gb[2]); add_packed_bf16x8(g + 8, gb[3]); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= g[i];
-    } else if (c.gate.data) {
+    } else if (c.gatep->data) {
         float g[16];
-        load16(c.gate, c.gate_vec, oy, ox, j0, 16, g);
+        load16(*c.gatep, c.gate_vec, oy, ox, c.ch0 + j0, 16, g);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= g[i];
     }
     if (rb) {                       // residual row prefetched as packed bf16 (see res_prefetch)
         float r[16];
         unpack_bf16x16(rb, r);
-        if (c.res.dtype == AIVC_BF16X2) { add_packed_bf16x8(r, rb[2]); add_packed_bf16x8(r + 8, rb[3]); }
+        if (c.resp->dtype == AIVC_BF16X2) { add_packed_bf16x8(r, rb[2]); add_packed_bf16x8(r + 8, rb[3]); }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
-    } else if (c.res.data) {
+    } else if (c.resp->data) {
         float r[16];
-        load16(c.res, c.res_vec, oy, ox, j0, 16, r);
+        load16(*c.resp, c.res_vec, oy, ox, c.ch0 + j0, 16, r);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
     }
@@ -399,8 +403,8 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
             v[4 * q] *= s.x; v[4 * q + 1] *= s.y; v[4 * q + 2] *= s.z; v[4 * q + 3] *= s.w;
         }
     }
-    if (interior && c.out_vec) store16_at(c.out, out_elem + j0, v);
-    else store16(c.out, c.out_vec, oy, ox, j0, 16, v);
+    if (interior && c.out_vec) store16_at(*c.outp, out_elem + j0, v);
+    else store16(*c.outp, c.out_vec, oy, ox, c.ch0 + j0, 16, v);
 }
 
 template <bool X2 = false>
@@ -420,29 +424,29 @@ __device__ __forceinline__ void fetch16(const FMap &m, size_t elem, int j0, uint
 template <int ACT, bool X2PIPE = false>
 __device__ __forceinline__ void epi_row(uint32_t taddr, int N, const float *sbias, const float *sscale,
                                         const EpiCtx &c, int oy, int ox, bool valid, int c_begin = 0) {
-    const bool interior = c.out.pad == 0 || (oy > 0 && oy < c.out.h - 1 && ox > 0 && ox < c.out.w - 1);
-    const size_t out_elem = valid ? fm_index(c.out, oy, ox, 0) : 0;
+    const bool interior = c.outp->pad == 0 || (oy > 0 && oy < c.outp->h - 1 && ox > 0 && ox < c.outp->w - 1);
+    const size_t out_elem = valid ? fm_index(*c.outp, oy, ox, c.ch0) : 0;
     // bf16 residual / gate rows are fetched one chunk ahead, so the L2 latency of chunk j+1 hides behind
     // the TMEM load and arithmetic of chunk j
     constexpr int NB = X2PIPE ? 4 : 2;
-    const bool pipe_res = valid && c.res.data && c.res_vec && (c.res.dtype == AIVC_BF16 || (X2PIPE && c.res.dtype == AIVC_BF16X2));
-    const bool pipe_gate = valid && c.gate.data && c.gate_vec && (c.gate.dtype == AIVC_BF16 || (X2PIPE && c.gate.dtype == AIVC_BF16X2));
-    const size_t res_elem = pipe_res ? fm_index(c.res, oy, ox, 0) : 0;
-    const size_t gate_elem = pipe_gate ? fm_index(c.gate, oy, ox, 0) : 0;
+    const bool pipe_res = valid && c.resp->data && c.res_vec && (c.resp->dtype == AIVC_BF16 || (X2PIPE && c.resp->dtype == AIVC_BF16X2));
+    const bool pipe_gate = valid && c.gatep->data && c.gate_vec && (c.gatep->dtype == AIVC_BF16 || (X2PIPE && c.gatep->dtype == AIVC_BF16X2));
+    const size_t res_elem = pipe_res ? fm_index(*c.resp, oy, ox, c.ch0) : 0;
+    const size_t gate_elem = pipe_gate ? fm_index(*c.gatep, oy, ox, c.ch0) : 0;
     uint4 rb[NB], rn[NB], gb[NB], gn[NB];
-    if (pipe_res) fetch16<X2PIPE>(c.res, res_elem, c_begin, rn);
-    if (pipe_gate) fetch16<X2PIPE>(c.gate, gate_elem, c_begin, gn);
+    if (pipe_res) fetch16<X2PIPE>(*c.resp, res_elem, c_begin, rn);
+    if (pipe_gate) fetch16<X2PIPE>(*c.gatep, gate_elem, c_begin, gn);
 #pragma unroll 1
     for (int j0 = c_begin; j0 < N; j0 += 16) {
         if (pipe_res) {
 #pragma unroll
             for (int i = 0; i < NB; ++i) rb[i] = rn[i];
-            if (j0 + 16 < N) fetch16<X2PIPE>(c.res, res_elem, j0 + 16, rn);
+            if (j0 + 16 < N) fetch16<X2PIPE>(*c.resp, res_elem, j0 + 16, rn);
         }
         if (pipe_gate) {
 #pragma unroll
             for (int i = 0; i < NB; ++i) gb[i] = gn[i];
-            if (j0 + 16 < N) fetch16<X2PIPE>(c.gate, gate_elem, j0 + 16, gn);
+            if (j0 + 16 < N) fetch16<X2PIPE>(*c.gatep, gate_elem, j0 + 16, gn);
         }
         float v[16];
         tmem_ld16(taddr + (uint32_t)j0, v);
