@@ -16,7 +16,7 @@ parity) timeout 600 python tools/parity_configs.py gpurun_out/r02_parity_configs
 fp32) timeout 600 python tools/fp32_engine_fps.py 2>/dev/null | tail -1 > gpurun_out/r02_fp32_engine.json; cat gpurun_out/r02_fp32_engine.json ;;
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_ncu_launches_3frames.csv python tools/frame_once.py 1 bf16x3 > gpurun_out/ncu_list.log 2>&1
-  for spec in "conv3x3_tc_kernel:c3_128_270:r02_conv3x3_x3" "conv3x3_tc_gdn_kernel:c3igdn_res_544:r02_conv3x3_gdn_x3" "conv_tc_kernel:up3_128_270:r02_convtc_up3_x3"; do
+  for spec in "conv3x3_tc_kernel:c3_128_270:r02_conv3x3_x3" "conv3x3_tc_gdn_kernel:c3igdn_res_544:r02_conv3x3_gdn_x3" "tconv3x3_tc_kernel:up3_128_270:r02_tconv3x3_x3"; do
     IFS=: read k case out <<< "$spec"
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o gpurun_out/$out python tools/bench_layer.py --precision bf16x3 --cases $case --iters 1 --reps 2 > gpurun_out/ncu_$out.log 2>&1
     ncu -i gpurun_out/$out.ncu-rep --page raw --csv > gpurun_out/${out}_ncu_raw.csv 2>/dev/null
