@@ -99,3 +99,41 @@ def test_reference_decoder_reads_the_cuda_encoders_golden_bitstream():
         for k in 'yuv':
             got = np.rint(dec[f][k].numpy() * 255).astype(np.uint8).reshape(-1)
             assert np.array_equal(got, fx['spec_rec_%s_%s' % (f, k)].reshape(-1)), (f, k)
+
+
+def test_synthetic_sources_of_the_config_fixtures_are_reproducible():
+    """tests/synth.py is integer-only, so the frames the BASELINE-configuration fixtures were minted from must come out
+    bit-identical on every machine and numpy build (a change here would make the GPU parity tests compare against
+    fixtures of different pictures)."""
+    import hashlib
+    from tests import synth
+    want = {(720, 3, 720, 1280): '58032c58517671812a3d80d01cd7dc46',
+            (1080, 3, 1080, 1920): '9751ef096fb0d2f6d111de30ed03a7ca',
+            (1081, 9, 1080, 1920): '7d9da5401645eacc704505c58583e209'}
+    for (seed, n, h, w), md5 in want.items():
+        clip = synth.clip(seed, n, h, w)
+        assert clip[0][0].shape == (h, w) and clip[0][1].shape == (h // 2, w // 2) and clip[0][0].dtype.name == 'uint8'
+        assert hashlib.md5(b''.join(p.tobytes() for fr in clip for p in fr)).hexdigest() == md5, (seed, n, h, w)
+
+
+def test_config_fixture_is_what_the_oracle_produces_here():
+    """The smallest BASELINE-configuration fixture (416x240 real frame, all intra, C=128) re-minted by the oracle on this
+    machine: same latent indices, same bytes, same planes as the committed tests/golden/cfg_bubbles240.npz."""
+    import hashlib
+    import os
+    import numpy as np
+    import torch
+    from aivc_b200 import models
+    from oracle import codec_ref as O
+    from tests import parity_cfg
+    fx = np.load(os.path.join(parity_cfg.GOLDEN, 'cfg_bubbles240.npz'))
+    y, u, v = parity_cfg.source_frames('bubbles240', fx)[0]
+    yuv = {k: torch.from_numpy(p.astype(np.float32) / 255.)[None, None] for k, p in zip('yuv', (y, u, v))}
+    net = models.build_standin(**parity_cfg.MODELS['bubbles240'])
+    z = O.zero_yuv(240, 416)
+    data, rec, aux = O.encode_frame(net, O.Tables(net), yuv, z, z, 0)
+    assert np.array_equal(aux['codec']['q'].numpy().astype(np.int32)[0], fx['frame_0_codec_q'].astype(np.int32))
+    assert np.array_equal(aux['codec']['z_hat'].numpy().astype(np.int32)[0], fx['frame_0_codec_z'].astype(np.int32))
+    assert hashlib.md5(data).hexdigest() == str(fx['frame_0_bytes_md5']) and len(data) == int(fx['frame_0_nbytes'])
+    planes = [np.rint(rec[k].numpy() * 255).astype(np.uint8)[0, 0] for k in 'yuv']
+    assert hashlib.md5(b''.join(p.tobytes() for p in planes)).hexdigest() == str(fx['frame_0_planes_md5'])
