@@ -609,8 +609,17 @@ def weights_version(module):
     return v
 
 
-def run_module(module, x, cfg=DEFAULT):
+def set_default_config(cfg):
+    """Config used by the drop-in modules' forward() (module(x)) from now on; returns the previous one.  The default is
+    Config() = the fp32-faithful split-bf16 tensor-core mode."""
+    global DEFAULT
+    old, DEFAULT = DEFAULT, cfg
+    return old
+
+
+def run_module(module, x, cfg=None):
     """forward() of the drop-in classes: NCHW fp32 CUDA tensor in, NCHW fp32 tensor out."""
+    cfg = DEFAULT if cfg is None else cfg
     if not (isinstance(x, torch.Tensor) and x.is_cuda):
         raise RuntimeError('aivc_b200 layers run on a CUDA device only (no CPU fallback); got '
                            + str(getattr(x, 'device', type(x))))

@@ -319,3 +319,39 @@ def test_edge_inputs_empty_latents_and_tiny_frames(precision, dev):
     assert sec == (1).to_bytes(4, 'big') + b'\x00'
     q = entropy.decode_y(sec[4:], np.ones((4, 2, 3), np.float32), 4, 2, 3)
     assert q.shape == (4, 2, 3) and not q.any()
+
+
+@pytest.mark.parametrize('size', [(80, 112), (135, 241)])
+def test_reference_style_decoder_on_the_dropin_modules(size, golden_dir, dev):
+    """The reference's decoder composition (real_life/decode.py:455-898, restated call for call in
+    tests/module_decoder.py) driven through the drop-in modules' own forward() on CUDA tensors -- the path a user gets
+    who lets the reference's Decoder run on the mirrors -- lands on the fused FrameCodec's reconstruction: exact fp32
+    engine on both sides, so the planes are identical (and, at 80x112, equal to the oracle's golden reconstruction)."""
+    from aivc_b200 import models, gop as G, plan
+    from aivc_b200.codec import FrameCodec, planes_to_device
+    from aivc_b200.plan import Config
+    from tests import module_decoder
+    h, w = size
+    net = models.build_standin(seed=4321, C=32, Cy=16, Cz=16, Csc=16).to(dev)
+    gop = G.generate_gop_struct('1_GOP_2')
+    if size == (80, 112):
+        fx = np.load(os.path.join(golden_dir, 'system_80x112.npz'))
+        clip = [[fx['src_frame_%d_%s' % (t, k)] for k in 'yuv'] for t in range(3)]
+    else:
+        rng = np.random.default_rng(8)
+        clip = [[rng.integers(0, 256, s, dtype=np.uint8) for s in ((h, w), ((h + 1) // 2, (w + 1) // 2), ((h + 1) // 2, (w + 1) // 2))]
+                for _ in range(3)]
+    frames = {'frame_%d' % t: planes_to_device(clip[t], dev) for t in range(3)}
+    cfg = Config(precision='fp32')
+    bts, rec = FrameCodec(net, h, w, dev, cfg).encode_gop(frames, gop)
+    old = plan.set_default_config(cfg)
+    try:
+        dec = module_decoder.decode_gop(net, bts, gop, h, w, dev)
+    finally:
+        plan.set_default_config(old)
+    for f in gop:
+        for k, p in zip('yuv', rec[f]):
+            got = torch.round(dec[f][k] * 255).to(torch.uint8).reshape(-1)
+            assert torch.equal(got, p), (f, k, int((got.int() - p.int()).abs().max()))
+            if size == (80, 112):
+                assert np.array_equal(got.cpu().numpy(), fx['spec_rec_%s_%s' % (f, k)].reshape(-1))
