@@ -59,6 +59,8 @@ struct Tc3Params {
     int ncta, nsplit;                 // output channels per work item; work items per pixel tile
     int act, post;
     int tiles_x, nitems;
+    int nfull;                        // pixel tiles [0, nfull) are whole tiles; SUB = 2 only: the tiles behind them are
+                                      // 16-row HALF tiles (one accumulator), see item_tile
     int in_pad;
     uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
@@ -78,6 +80,37 @@ __device__ __forceinline__ void chunk_coords(const Tc3Params &p, int kc, int &ca
         ca = j * 64 + (part == 1 ? p.a_lo : 0);
         cb = j * 64 + (part == 2 ? p.b_lo : 0);
     }
+}
+
+// Work item -> pixel tile of conv3x3_tc_kernel; returns the number of 128-row accumulators (sub-tiles) in use.
+// Whole tiles are numbered row-major over the image in bands of tile_h rows.  A layer whose whole tiles fill a
+// fraction of the last wave (270x480: 510 tiles of 32x8 on 148 SMs = 3.45 waves, paid as 4) is cut differently by
+// the host: nfull = a multiple of the grid size whole tiles, and the rest of the image as 16-row half tiles -- the
+// remaining columns of the band the whole tiles end in, then the 16-row bands below it -- so that the last wave
+// costs half a tile per SM (3.5 tile times instead of 4).  Items are dealt round-robin, nfull % grid == 0.
+__device__ __forceinline__ int item_tile(const Tc3Params &p, int item, int tile_h, int &y0, int &x0, int &n0) {
+    const int tile = item / p.nsplit;
+    n0 = (item - tile * p.nsplit) * p.ncta;
+    if (tile < p.nfull) {
+        y0 = (tile / p.tiles_x) * tile_h;
+        x0 = (tile % p.tiles_x) * TILE_W;
+        return tile_h >> 4;
+    }
+    int k = tile - p.nfull;
+    const int fb = p.nfull / p.tiles_x, xf = p.nfull - fb * p.tiles_x;
+    const int part = xf ? 2 * (p.tiles_x - xf) : 0;            // half tiles that complete band fb
+    int urow, col;
+    if (k < part) {
+        col = xf + (k >> 1);
+        urow = 2 * fb + (k & 1);
+    } else {
+        k -= part;
+        urow = 2 * fb + (xf ? 2 : 0) + k / p.tiles_x;
+        col = k % p.tiles_x;
+    }
+    y0 = urow * 16;
+    x0 = col * TILE_W;
+    return 1;
 }
 
 // 16 channels of this thread's pixel as packed bf16 (two 16-byte loads)
@@ -182,11 +215,10 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
     bool store_pending = false;
     for (int u = first; u < nunits; u += stride, ++it) {
         const uint32_t buf = it & 1u;
-        const int tile = u / p.nsplit;
-        const int n0 = (u - tile * p.nsplit) * N;
-        const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
+        int y0, x0, n0;
+        const bool active = j < item_tile(p, u, TILE_H, y0, x0, n0);      // (half tiles: the j = 1 teams only hand the buffer back)
         const int oy = y0 + 16 * j + row / TILE_W, ox = x0 + row % TILE_W;
-        const bool valid = (oy < p.out.h) && (ox < p.out.w);
+        const bool valid = active && (oy < p.out.h) && (ox < p.out.w);
         const bool use_res = res_fast && valid;
         ctx.ch0 = n0;                                             // (channels [n0, n0 + N) of out / res / gate)
         const __nv_bfloat16 *res_px = use_res ? (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0) : nullptr;
@@ -202,7 +234,7 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
         mbar_wait(&acc_full[buf], (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(128 * SUB) + (uint32_t)(j * 128);
-        if (c_lo < N) {
+        if (c_lo < N && active) {
             if (p.tma_store) {
                 const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
                 for (int ch0 = c_lo; ch0 < c_hi; ch0 += 32) {
@@ -283,8 +315,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0;          // ring slot / phase, advanced incrementally
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-                const int tile = item / p.nsplit, n0 = (item - tile * p.nsplit) * N;
-                const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
+                int y0, x0, n0;
+                item_tile(p, item, TILE_H, y0, x0, n0);
                 for (int kc = 0; kc < p.kv; ++kc) {
                     int ca, cb;
                     chunk_coords(p, kc, ca, cb);
@@ -316,6 +348,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0, it = 0;
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
                 const uint32_t buf = it & 1u;
+                int y0_, x0_, n0_;
+                const int nsub = item_tile(p, item, TILE_H, y0_, x0_, n0_);
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);     // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * (uint32_t)(128 * SUB);
@@ -333,6 +367,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 const uint64_t bdesc = make_desc(g_addr + kx * p.b_slot, 128);
 #pragma unroll
                                 for (int j = 0; j < SUB; ++j) {
+                                    if (SUB > 1 && j >= nsub) break;
                                     const uint32_t start = a_addr + (uint32_t)((ky + 16 * j) * PATCH_W + kx) * 128u;
                                     const uint64_t adesc = a_tmpl | (uint64_t)((start >> 4) & 0x3FFF);
 #pragma unroll
@@ -1025,7 +1060,21 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
     p.ncta = cout / p.nsplit;
     p.act = op->act; p.post = op->post;
-    p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.in_pad = op->in.pad;
+    p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.nfull = ntiles; p.in_pad = op->in.pad;
+    if (sub == 2 && x3 && !gdn) {
+        // whole tiles for as many full waves as the image holds, the rest as 16-row half tiles (item_tile) when that
+        // shortens the step.  Costs in half-tile units; a half tile is dearer than half a whole one (every weight
+        // group feeds half as many MMAs, so the two-deep group ring runs latency-bound: measured at 270x480, three
+        // whole tiles + one half tile per SM take 92.5 us against 96.5 us for four whole ones).
+        const int G = sm_count_cached();
+        const int urows = ceil_div(op->out.h, 16), units = urows * tiles_x;
+        const int q = units / (2 * G), nfull = q * G, nhalf = units - 2 * nfull;
+        const double mixed = 2.0 * q + 1.5 * ceil_div(nhalf, G), whole = 2.0 * ceil_div(ntiles, G);
+        if (q > 0 && nfull <= (urows / 2) * tiles_x && mixed < whole - 0.25) {
+            p.nfull = nfull;
+            p.nitems = nfull + nhalf;
+        }
+    }
     p.b_bytes = (uint32_t)p.ncta * 128u;                       // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;
