@@ -667,9 +667,15 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         for (int e = 0; e < 4; ++e) {
                             const float xx = v[4 * q + e] + bb[e];
                             const float t = nr[4 * q + e] + ee[e];
-                            if (p.x3) {                                         // fp32-faithful mode: IEEE sqrt / division
-                                const float sq = sqrtf(t);
-                                v[4 * q + e] = inverse ? xx * sq : xx / sq;
+                            if (p.x3) {
+                                // fp32-faithful mode: MUFU.RSQ + one Newton step = t^-1/2 to ~1 ulp (the operands
+                                // carry 2^-17 already), a quarter of the instructions of IEEE sqrt + division,
+                                // which made pass 2 the longest link of this kernel's chain.  t >= beta_bound^2 > 0.
+                                float rs;
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+                                const float ht = 0.5f * t;
+                                rs = fmaf(rs, fmaf(-ht * rs, rs, 0.5f), rs);
+                                v[4 * q + e] = inverse ? xx * (t * rs) : xx * rs;
                             } else {
                                 float rs;                                       // MUFU.RSQ: 2^-22 relative, far below bf16
                                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));

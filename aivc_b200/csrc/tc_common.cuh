@@ -160,6 +160,37 @@ __device__ __forceinline__ bool fmap_vec_ok(const FMap &m) {
     return (m.c_off % al == 0) && (m.c_stride % al == 0) && (((uintptr_t)m.data & 15) == 0);
 }
 
+// 32-byte global accesses (sm_100: LDG / STG .256): a thread's 16 channels of bf16 in ONE instruction and one full
+// sector, where two 16-byte accesses cost the load / store unit two passes over the warp's 32 lines
+__device__ __forceinline__ bool aligned32(const void *p) { return ((uintptr_t)p & 31) == 0; }
+__device__ __forceinline__ void stg256(void *p, const uint32_t *w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+// 16 packed 16-bit channels at p (16-byte aligned at least)
+__device__ __forceinline__ void ldg_16ch(const void *p, uint4 &a, uint4 &b) {
+    if (aligned32(p)) {
+        ldg256(p, a, b);
+    } else {
+        a = reinterpret_cast<const uint4 *>(p)[0];
+        b = reinterpret_cast<const uint4 *>(p)[1];
+    }
+}
+__device__ __forceinline__ void stg_16ch(void *p, const uint32_t *w) {
+    if (aligned32(p)) {
+        stg256(p, w);
+    } else {
+        reinterpret_cast<uint4 *>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4 *>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // 16 floats -> split bf16: hi[8] / lo[8] packed words (see AIVC_BF16X2)
 __device__ __forceinline__ void split16(const float *v, uint32_t *hi, uint32_t *lo) {
 #pragma unroll
@@ -191,7 +222,8 @@ __device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, in
                 v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
             }
         } else {
-            const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + base);
+            uint4 p[2];
+            ldg_16ch((const __nv_bfloat16 *)m.data + base, p[0], p[1]);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const uint4 t = p[i];
@@ -203,7 +235,8 @@ __device__ __forceinline__ void load16(const FMap &m, bool vec, int y, int x, in
                 }
             }
             if (m.dtype == AIVC_BF16X2) {                      // + lo half
-                const uint4 *pl = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + base + (m.c_stride >> 1));
+                uint4 pl[2];
+                ldg_16ch((const __nv_bfloat16 *)m.data + base + (m.c_stride >> 1), pl[0], pl[1]);
                 add_packed_bf16x8(v, pl[0]);
                 add_packed_bf16x8(v + 8, pl[1]);
             }
@@ -336,19 +369,13 @@ __device__ __forceinline__ void store16_at(const FMap &m, size_t elem, const flo
     } else if (m.dtype == AIVC_BF16X2) {
         uint32_t w[8], l[8];
         split16(v, w, l);
-        uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem);
-        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        q[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        uint4 *ql = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem + (m.c_stride >> 1));
-        ql[0] = make_uint4(l[0], l[1], l[2], l[3]);
-        ql[1] = make_uint4(l[4], l[5], l[6], l[7]);
+        stg_16ch((__nv_bfloat16 *)m.data + elem, w);
+        stg_16ch((__nv_bfloat16 *)m.data + elem + (m.c_stride >> 1), l);
     } else {
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = pack16x2(v[2 * i], v[2 * i + 1], m.dtype == AIVC_F16);
-        uint4 *q = reinterpret_cast<uint4 *>((__nv_bfloat16 *)m.data + elem);
-        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        stg_16ch((__nv_bfloat16 *)m.data + elem, w);
     }
 }
 
@@ -409,14 +436,9 @@ __device__ __forceinline__ void epi_tail16(float *v, const EpiCtx &c, const floa
 
 template <bool X2 = false>
 __device__ __forceinline__ void fetch16(const FMap &m, size_t elem, int j0, uint4 *rb) {
-    const uint4 *p = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0);
-    rb[0] = p[0];
-    rb[1] = p[1];
-    if (X2 && m.dtype == AIVC_BF16X2) {                        // lo halves of a split map
-        const uint4 *pl = reinterpret_cast<const uint4 *>((const __nv_bfloat16 *)m.data + elem + j0 + (m.c_stride >> 1));
-        rb[2] = pl[0];
-        rb[3] = pl[1];
-    }
+    ldg_16ch((const __nv_bfloat16 *)m.data + elem + j0, rb[0], rb[1]);
+    if (X2 && m.dtype == AIVC_BF16X2)                          // lo halves of a split map
+        ldg_16ch((const __nv_bfloat16 *)m.data + elem + j0 + (m.c_stride >> 1), rb[2], rb[3]);
 }
 
 // X2PIPE: also pipeline split-bf16 residual / gate rows (8 more registers per row in flight: only kernels with
