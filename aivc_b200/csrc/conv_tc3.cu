@@ -64,8 +64,11 @@ struct Tc3Params {
     int in_pad;
     uint32_t b_bytes, b_slot;         // one tap's weight slice (ncta x 64 ch) and its 1 KB-rounded slot
     int ng;                           // weight-group ring depth
-    int tma_store;                    // epilogue stores through smem + TMA (bf16, 32-channel multiples)
+    int tma_store;                    // epilogue stores through smem + TMA: 1 = bf16 (32-channel multiples), 2 = split
+                                      // bf16 (16-channel chunks, hi and lo tiles; o_lo = channel coordinate of lo)
+    int o_lo;
     int skip_lo;                      // split-bf16 input with all-zero lo halves (AIVC_OP_IN_EXACT): no lo.Whi part
+    int nsteps;                       // conv3x3_tc_kernel: patch steps per tile (patch_step)
     int x3, kv, a_lo, b_lo;           // split-bf16 operands (AIVC_ENGINE_TC_X3): kv = 3 * kchunks virtual chunks
                                       // (hi.Whi, lo.Whi, hi.Wlo); channel coordinates of the lo halves
 };
@@ -80,6 +83,23 @@ __device__ __forceinline__ void chunk_coords(const Tc3Params &p, int kc, int &ca
         ca = j * 64 + (part == 1 ? p.a_lo : 0);
         cb = j * 64 + (part == 2 ? p.b_lo : 0);
     }
+}
+
+// conv3x3_tc_kernel walks the contraction patch by patch: step s loads ONE activation patch (channel coordinate ca)
+// and runs it against one or two weight sets (channel coordinates cb[0..n)).  Split bf16: the hi patch of a 64-channel
+// chunk meets Whi and Wlo, the lo patch meets Whi -- four patch loads per 128 input channels where the plain order
+// of virtual chunks (chunk_coords) needs six, and twice the tensor time per hi patch to fetch the next one behind.
+__device__ __forceinline__ int patch_step(const Tc3Params &p, int s, int &ca, int (&cb)[2]) {
+    if (!p.x3) {
+        ca = cb[0] = cb[1] = s * 64;
+        return 1;
+    }
+    const int per = p.skip_lo ? 1 : 2, j = s / per;
+    const bool lo = s - j * per == 1;
+    ca = j * 64 + (lo ? p.a_lo : 0);
+    cb[0] = j * 64;
+    cb[1] = j * 64 + p.b_lo;
+    return lo ? 1 : 2;
 }
 
 // Work item -> pixel tile of conv3x3_tc_kernel; returns the number of 128-row accumulators (sub-tiles) in use.
@@ -192,6 +212,44 @@ __device__ __forceinline__ void chunk32_to_stage(const Tc3Params &p, uint32_t ta
     }
 }
 
+// Split-bf16 form: one 16-channel chunk of an accumulator row -> bias, activation, residual (loaded in place), post,
+// scale -> hi and lo bf16 -> two 32-byte rows of the team's staging tile ([128 rows x 32 B hi | 128 rows x 32 B lo],
+// 32B swizzle), which leave as two TMA stores.  Per-thread global stores of a row's 32-byte pieces (32 lines per warp
+// instruction) cost this MMA-bound kernel 18 % (270x480: 91 us against 75 us with the stores removed): they crowd
+// the memory pipe the single MMA-issuing and TMA-issuing threads poll their barriers through.
+template <int ACT>
+__device__ __forceinline__ void chunk16_x3_to_stage(const Tc3Params &p, const EpiCtx &ctx, uint32_t taddr, int j0, int n0,
+                                                    const float *sbias, const float *sscale, int oy, int ox, bool valid,
+                                                    bool edge, uint8_t *stage, int row) {
+    float v[16];
+    tmem_ld16(taddr + (uint32_t)j0, v);
+    epi_bias_act16<ACT>(v, sbias, n0 + j0, 0, true);
+    if (p.res.data && valid) {
+        float r[16];
+        load16(p.res, ctx.res_vec, oy, ox, n0 + j0, 16, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
+    }
+    post_apply16(p.post, v);
+    if (p.out_scale) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(sscale + n0 + j0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 sc = s4[q];
+            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+        }
+    }
+    uint32_t w[8], l[8];
+    split16(v, w, l);
+    uint32_t off = (uint32_t)(row * 32);
+    off ^= ((off >> 7) & 1u) << 4;                              // 32B swizzle, as the TMA store expects
+    *reinterpret_cast<uint4 *>(stage + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4 *>(stage + (off ^ 16u)) = make_uint4(w[4], w[5], w[6], w[7]);
+    *reinterpret_cast<uint4 *>(stage + 4096 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(stage + 4096 + (off ^ 16u)) = make_uint4(l[4], l[5], l[6], l[7]);
+    if (edge) store16(p.out, ctx.out_vec, oy, ox, n0 + j0, 16, v);       // border replicas (and the pixel once more)
+}
+
 template <int SUB, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensorMap *tmO, uint8_t *stage,
                                               const float *sbias, const float *sscale, uint64_t *acc_full,
@@ -234,7 +292,24 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
         mbar_wait(&acc_full[buf], (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(128 * SUB) + (uint32_t)(j * 128);
-        if (c_lo < N && active) {
+        if (c_lo < N && active && p.tma_store == 2) {
+            const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
+            for (int ch0 = c_lo; ch0 < c_hi; ch0 += 16) {
+                if (store_pending) {                           // staging tile still being read by the last stores?
+                    if (leader) tma_store_wait_read();
+                    named_bar_sync(1 + team, 128);
+                }
+                chunk16_x3_to_stage<ACT>(p, ctx, tl, ch0, n0, sbias, sscale, oy, ox, valid, edge, my_stage, row);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(1 + team, 128);
+                if (leader) {
+                    tma_store_3d(tmO, my_stage, n0 + ch0, x0, y0 + 16 * j);
+                    tma_store_3d(tmO, my_stage + 4096, p.o_lo + n0 + ch0, x0, y0 + 16 * j);
+                    tma_store_commit();
+                }
+                store_pending = true;
+            }
+        } else if (c_lo < N && active) {
             if (p.tma_store) {
                 const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
                 for (int ch0 = c_lo; ch0 < c_hi; ch0 += 32) {
@@ -317,20 +392,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
                 int y0, x0, n0;
                 item_tile(p, item, TILE_H, y0, x0, n0);
-                for (int kc = 0; kc < p.kv; ++kc) {
-                    int ca, cb;
-                    chunk_coords(p, kc, ca, cb);
+                for (int st = 0; st < p.nsteps; ++st) {
+                    int ca, cb[2];
+                    const int nsets = patch_step(p, st, ca, cb);
                     mbar_wait(&a_empty[sa], pa ^ 1u);
                     mbar_expect_tx(&a_full[sa], PATCH_BYTES);
                     tma_load_3d(a_ring + sa * A_SLOT, &tmA, &a_full[sa], ca, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
-                    for (int ky = 0; ky < 3; ++ky) {
+                    for (int g = 0; g < 3 * nsets; ++g) {
+                        const int ky = g >= 3 ? g - 3 : g;
                         mbar_wait(&g_empty[sg], pg ^ 1u);
                         mbar_expect_tx(&g_full[sg], 3u * p.b_bytes);
                         uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx)
-                            tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], cb, n0, ky * 3 + kx);
+                            tma_load_3d(dst + kx * p.b_slot, &tmB, &g_full[sg], cb[g >= 3], n0, ky * 3 + kx);
                         if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                     }
                 }
@@ -354,10 +430,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * (uint32_t)(128 * SUB);
                 uint32_t accum = 0;
-                for (int kc = 0; kc < p.kv; ++kc) {
+                for (int st = 0; st < p.nsteps; ++st) {
+                    int ca_, cb_[2];
+                    const int ngroups = 3 * patch_step(p, st, ca_, cb_);
                     mbar_wait(&a_full[sa], pa);
                     const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
-                    for (int ky = 0; ky < 3; ++ky) {
+                    for (int g = 0; g < ngroups; ++g) {
+                        const int ky = g >= 3 ? g - 3 : g;
                         mbar_wait(&g_full[sg], pg);
                         tc_fence_after();
                         const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
@@ -1062,6 +1141,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.cout = cout; p.kchunks = cin / 64;
     p.skip_lo = (x3 && (op->flags & AIVC_OP_IN_EXACT)) ? 1 : 0;
     p.x3 = x3 ? 1 : 0; p.kv = (x3 ? (p.skip_lo ? 2 : 3) : 1) * p.kchunks; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
+    p.nsteps = (x3 && !p.skip_lo ? 2 : 1) * p.kchunks;
     // small layers (SUB = 1): output channels split over two work items, two CTAs per SM, shallow weight ring
     p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
     p.ncta = cout / p.nsplit;
@@ -1122,7 +1202,18 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
                                      ((uintptr_t)rs.data & 15) == 0);
     p.tma_store = (!x3 && o.dtype == AIVC_BF16 && o.c_off % 8 == 0 && o.c_stride % 8 == 0 && p.ncta % 32 == 0 &&
                    ((uintptr_t)o.data & 15) == 0 && !op->gate.data && res_ok) ? 1 : 0;
-    if (p.tma_store) {
+    // (the 16-row-tile form of the kernel runs the small, latency-bound layers: per-thread stores there)
+    if (x3 && !gdn && sub == 2 && o.dtype == AIVC_BF16X2 && o.c_off % 8 == 0 && o.c_stride % 16 == 0 && p.ncta % 32 == 0 &&
+        ((uintptr_t)o.data & 15) == 0 && !op->gate.data && (!rs.data || rs.dtype == AIVC_BF16X2 || rs.dtype == AIVC_BF16)) {
+        p.tma_store = 2;
+        p.o_lo = o.c_stride / 2;
+        const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
+        cuuint64_t dims[3] = {(cuuint64_t)(p.o_lo + cout), (cuuint64_t)o.w, (cuuint64_t)o.h};  // hi and lo halves of the interior
+        cuuint64_t strides[2] = {opix, orow};
+        cuuint32_t box[3] = {16, TILE_W, 16};
+        void *base = (char *)o.data + ((size_t)o.pad * o.pitch + o.pad) * opix + (size_t)o.c_off * 2;
+        if (encode_map(&tmO, base, 3, dims, strides, box, 32, "O/3x3 split")) return 1;
+    } else if (p.tma_store) {
         const size_t opix = (size_t)o.c_stride * 2, orow = (size_t)o.pitch * opix;
         cuuint64_t dims[3] = {(cuuint64_t)cout, (cuuint64_t)o.w, (cuuint64_t)o.h};     // interior only: OOB rows/cols are clipped
         cuuint64_t strides[2] = {opix, orow};
@@ -1132,7 +1223,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     }
     const size_t smem = fixed + (size_t)p.ng * 3 * p.b_slot;
     const int sm_count = sm_count_cached();
-    const bool res = p.tma_store && rs.data;                 // residual prefetched into registers
+    const bool res = p.tma_store == 1 && rs.data;            // residual prefetched into registers
     g_aivc_kernel_class = gdn ? AIVC_KC_TC3_GDN : AIVC_KC_TC3;
     if (gdn) {
         CUtensorMap tmG;
