@@ -285,6 +285,14 @@ __device__ __forceinline__ void epilogue_team(const Tc3Params &p, const CUtensor
 #pragma unroll
             for (int i = 0; i < 4; ++i) rr[i] = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (p.tma_store == 2 && p.res.data && valid && c_lo < N) {
+            // split-bf16 residual rows (loaded in place, 16 channels at a time, chunk16_x3_to_stage): this thread's
+            // hi and lo lines are asked into L2 while the tensor pipe still works on the tile, so that the four
+            // dependent loads behind the wait are L2 hits (the residual was written two layers ago: HBM by now)
+            const __nv_bfloat16 *r = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, n0 + c_lo);
+            prefetch_l2(r);
+            if (p.res.dtype == AIVC_BF16X2) prefetch_l2(r + (p.res.c_stride >> 1));
+        }
         if (use_res && c_lo < N) {                              // first 32 channels: issued before the wait
             ldg_bf16x16(res_px + c_lo, rr[0], rr[1]);
             ldg_bf16x16(res_px + c_lo + 16, rr[2], rr[3]);
@@ -675,6 +683,11 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const bool use_res = RES && valid;
             const bool edge = valid && p.out.pad != 0 && (oy == 0 || oy == p.out.h - 1 || ox == 0 || ox == p.out.w - 1);
             const size_t out_elem = valid ? fm_index(p.out, oy, ox, 0) : 0;
+            if (p.x3 && p.res.data && valid) {                 // split-bf16 residual rows (loaded in place in pass 2): into L2 now
+                const __nv_bfloat16 *r = (const __nv_bfloat16 *)p.res.data + fm_index(p.res, oy, ox, c_lo);
+                prefetch_l2(r);
+                if (p.res.dtype == AIVC_BF16X2) prefetch_l2(r + (p.res.c_stride >> 1));
+            }
             // ---- pass 1: (acc + bias)^2 -> packed bf16 in TMEM (A operand of the norm GEMM)
             mbar_wait(&bars.acc_full[buf], (it >> 1) & 1u);
             mbar_wait(&bars.xsq_empty, (it & 1u) ^ 1u);        // norm MMAs of the previous tile have read x^2

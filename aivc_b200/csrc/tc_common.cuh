@@ -173,6 +173,7 @@ __device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p));
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 16 packed 16-bit channels at p (16-byte aligned at least)
 __device__ __forceinline__ void ldg_16ch(const void *p, uint4 &a, uint4 &b) {
     if (aligned32(p)) {
@@ -306,7 +307,7 @@ struct EpiCtx {
     int ch0;
     int post, act_channels;
     bool has_scale, out_vec, res_vec, gate_vec;
-    bool precise;       // bf16x3 mode: IEEE sigmoid / sqrt / division instead of the fast approximations
+    bool precise;       // bf16x3 mode: accurate expf in the sigmoid (see epi_bias_act16)
 };
 
 __device__ __forceinline__ EpiCtx make_epi(const FMap &out, const FMap &res, const FMap &gate, int post,
@@ -344,10 +345,17 @@ __device__ __forceinline__ void epi_bias_act16(float *v, const float *sbias, int
         const float4 b = b4[q];
         v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
-    if (ACT == AIVC_ACT_SIGMOID && act_channels == 0 && !precise) {
-        // bf16 engine: ex2.approx + rcp.approx (2^-22 relative) instead of expf + IEEE division
+    if (ACT == AIVC_ACT_SIGMOID && act_channels == 0) {
+        // ex2.approx + rcp.approx (2^-22 relative) instead of expf + IEEE division; the split-bf16 mode keeps the
+        // accurate expf (its operands carry 2^-17: the approximate reciprocal's 2 ulp are far below that, an IEEE
+        // division's slow path is half of this epilogue's instructions)
+        if (precise) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+            for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + expf(-v[i]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+        }
     } else if (ACT != AIVC_ACT_NONE) {
         if (act_channels == 0 || j0 + 16 <= act_channels) {
 #pragma unroll
