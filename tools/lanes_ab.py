@@ -1,6 +1,7 @@
 """A/B: frames in flight (1 | 2), both tensor-core precisions.  One 1080p RA GOP encode + decode, resident inputs.
 Measured on B200 (round 2): bf16x3 23.6 -> 23.9 frames/s, bf16 60.5 -> 61.3 (with programmatic dependent launch
-switched off as well: 23.8 / 61.6) -- the device is 95 % busy and power-capped with one frame in flight."""
+switched off as well: 23.8 / 61.6); after the epilogue rework: bf16x3 28.1 -> 28.4 -- the device is 95 % busy and
+power-capped with one frame in flight."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
