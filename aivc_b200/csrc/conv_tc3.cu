@@ -69,26 +69,14 @@ struct Tc3Params {
     int o_lo;
     int skip_lo;                      // split-bf16 input with all-zero lo halves (AIVC_OP_IN_EXACT): no lo.Whi part
     int nsteps;                       // conv3x3_tc_kernel: patch steps per tile (patch_step)
-    int x3, kv, a_lo, b_lo;           // split-bf16 operands (AIVC_ENGINE_TC_X3): kv = 3 * kchunks virtual chunks
-                                      // (hi.Whi, lo.Whi, hi.Wlo); channel coordinates of the lo halves
+    int x3, a_lo, b_lo;               // split-bf16 operands (AIVC_ENGINE_TC_X3): hi.Whi + lo.Whi + hi.Wlo; channel
+                                      // coordinates of the lo halves of the activations / weights
 };
 
-// virtual chunk -> channel coordinates of the activation patch and of the weight slice
-__device__ __forceinline__ void chunk_coords(const Tc3Params &p, int kc, int &ca, int &cb) {
-    ca = cb = kc * 64;
-    if (p.x3) {
-        int part = kc / p.kchunks;
-        const int j = kc - part * p.kchunks;
-        if (p.skip_lo && part == 1) part = 2;                   // (two parts only: hi.Whi, hi.Wlo)
-        ca = j * 64 + (part == 1 ? p.a_lo : 0);
-        cb = j * 64 + (part == 2 ? p.b_lo : 0);
-    }
-}
-
-// conv3x3_tc_kernel walks the contraction patch by patch: step s loads ONE activation patch (channel coordinate ca)
+// conv3x3_tc_kernel and conv3x3_tc_gdn_kernel walk the contraction patch by patch: step s loads ONE activation patch (channel coordinate ca)
 // and runs it against one or two weight sets (channel coordinates cb[0..n)).  Split bf16: the hi patch of a 64-channel
 // chunk meets Whi and Wlo, the lo patch meets Whi -- four patch loads per 128 input channels where the plain order
-// of virtual chunks (chunk_coords) needs six, and twice the tensor time per hi patch to fetch the next one behind.
+// of virtual chunks (hi.Whi, lo.Whi, hi.Wlo over all channels) needs six, and twice the tensor time per hi patch to fetch the next one behind.
 __device__ __forceinline__ int patch_step(const Tc3Params &p, int s, int &ca, int (&cb)[2]) {
     if (!p.x3) {
         ca = cb[0] = cb[1] = s * 64;
@@ -576,20 +564,21 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             uint32_t sa = 0, pa = 0, sg = 0, pg = 0;
             for (int tile = blockIdx.x; tile < p.nitems; tile += gridDim.x) {
                 const int y0 = (tile / p.tiles_x) * TILE_H, x0 = (tile % p.tiles_x) * TILE_W;
-                for (int kc = 0; kc < p.kv; ++kc) {
-                    int ca, cb;
-                    chunk_coords(p, kc, ca, cb);
+                for (int st = 0; st < p.nsteps; ++st) {                          // patch by patch, see patch_step
+                    int ca, cb[2];
+                    const int nsets = patch_step(p, st, ca, cb);
                     mbar_wait(&bars.a_empty[sa], pa ^ 1u);
                     mbar_expect_tx(&bars.a_full[sa], PATCH_BYTES);
                     tma_load_3d(a_ring + sa * A_SLOT, &tmA, &bars.a_full[sa], ca, x0 - 1 + p.in_pad, y0 - 1 + p.in_pad);
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
-                    for (int ky = 0; ky < 3; ++ky) {
+                    for (int g = 0; g < 3 * nsets; ++g) {
+                        const int ky = g >= 3 ? g - 3 : g;
                         mbar_wait(&bars.g_empty[sg], pg ^ 1u);
                         mbar_expect_tx(&bars.g_full[sg], 3u * p.b_bytes);
                         uint8_t *dst = g_ring + sg * g_slot;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx)
-                            tma_load_3d(dst + kx * p.b_slot, &tmB, &bars.g_full[sg], cb, 0, ky * 3 + kx);
+                            tma_load_3d(dst + kx * p.b_slot, &tmB, &bars.g_full[sg], cb[g >= 3], 0, ky * 3 + kx);
                         if (++sg == (uint32_t)p.ng) { sg = 0; pg ^= 1u; }
                     }
                 }
@@ -627,10 +616,13 @@ conv3x3_tc_gdn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * 128u;
                 uint32_t accum = 0;
-                for (int kc = 0; kc < p.kv; ++kc) {
+                for (int st = 0; st < p.nsteps; ++st) {
+                    int ca_, cb_[2];
+                    const int ngroups = 3 * patch_step(p, st, ca_, cb_);
                     mbar_wait(&bars.a_full[sa], pa);
                     const uint32_t a_addr = smem_u32(a_ring + sa * A_SLOT);
-                    for (int ky = 0; ky < 3; ++ky) {
+                    for (int g = 0; g < ngroups; ++g) {
+                        const int ky = g >= 3 ? g - 3 : g;
                         mbar_wait(&bars.g_full[sg], pg);
                         tc_fence_after();
                         const uint32_t g_addr = smem_u32(g_ring + sg * g_slot);
@@ -1153,7 +1145,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.bias = op->bias; p.out_scale = op->out_scale;
     p.cout = cout; p.kchunks = cin / 64;
     p.skip_lo = (x3 && (op->flags & AIVC_OP_IN_EXACT)) ? 1 : 0;
-    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? (p.skip_lo ? 2 : 3) : 1) * p.kchunks; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
+    p.x3 = x3 ? 1 : 0; p.a_lo = op->in.c_stride / 2; p.b_lo = cin;
     p.nsteps = (x3 && !p.skip_lo ? 2 : 1) * p.kchunks;
     // small layers (SUB = 1): output channels split over two work items, two CTAs per SM, shallow weight ring
     p.nsplit = (sub == 1 && !gdn && cout == 128 && ntiles < 296) ? 2 : 1;
@@ -1276,7 +1268,7 @@ int tconv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.out = to_dev(o);
     p.bias = op->bias;
     p.cout = cout; p.ncta = cout; p.nsplit = 1; p.kchunks = cin / 64;
-    p.x3 = x3 ? 1 : 0; p.kv = (x3 ? 3 : 1) * p.kchunks; p.a_lo = in.c_stride / 2; p.b_lo = cin;
+    p.x3 = x3 ? 1 : 0; p.a_lo = in.c_stride / 2; p.b_lo = cin;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles;
     p.b_bytes = (uint32_t)cout * 128u;
