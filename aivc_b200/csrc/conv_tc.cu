@@ -241,9 +241,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_tc_kernel(const __grid_const
                 for (int i = 0; i < 16; ++i) {
                     const float x = v[i] + sbias[j0 + i];
                     const float t = nrm[i] + sbeta[j0 + i];
-                    if (p.x3) {                                 // fp32-faithful mode: IEEE sqrt and division
-                        const float sq = sqrtf(t);
-                        v[i] = (p.gdn == 1) ? x / sq : x * sq;
+                    if (p.x3) {                                 // fp32-faithful mode: as conv3x3_tc_gdn_kernel, MUFU.RSQ +
+                        float rs = rsqrtf(t);                   // one Newton step = t^-1/2 to ~1 ulp
+                        const float ht = 0.5f * t;
+                        rs = fmaf(rs, fmaf(-ht * rs, rs, 0.5f), rs);
+                        v[i] = (p.gdn == 1) ? x * rs : x * (t * rs);
                     } else {
                         const float rs = rsqrtf(t);             // MUFU.RSQ: 2^-22 relative, far below bf16
                         v[i] = (p.gdn == 1) ? x * rs : x * (t * rs);
