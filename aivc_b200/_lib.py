@@ -50,6 +50,7 @@ _SIGS = {
     'aivc_profile_read': (C.c_int, [C.POINTER(C.c_double)]),
     'aivc_profile_dump': (C.c_int, [C.c_char_p]),
     'aivc_profile_read_classes': (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    'aivc_debug_tc3_tiling': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     'aivc_pack_conv_weight': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     'aivc_packed_weight_bytes': (C.c_size_t, [C.c_int] * 4),

@@ -96,7 +96,7 @@ __device__ __forceinline__ int patch_step(const Tc3Params &p, int s, int &ca, in
 // the host: nfull = a multiple of the grid size whole tiles, and the rest of the image as 16-row half tiles -- the
 // remaining columns of the band the whole tiles end in, then the 16-row bands below it -- so that the last wave
 // costs half a tile per SM (3.5 tile times instead of 4).  Items are dealt round-robin, nfull % grid == 0.
-__device__ __forceinline__ int item_tile(const Tc3Params &p, int item, int tile_h, int &y0, int &x0, int &n0) {
+__host__ __device__ __forceinline__ int item_tile(const Tc3Params &p, int item, int tile_h, int &y0, int &x0, int &n0) {
     const int tile = item / p.nsplit;
     n0 = (item - tile * p.nsplit) * p.ncta;
     if (tile < p.nfull) {
@@ -1115,6 +1115,41 @@ static int sm_count_cached() {
     return sm_count;
 }
 
+// Split-bf16 stages on 32-row tiles: whole tiles for as many full waves as the image holds, the rest as 16-row half
+// tiles (item_tile) when that shortens the step.  Costs in half-tile units; a half tile is dearer than half a whole
+// one (every weight group feeds half as many MMAs, so the two-deep group ring runs latency-bound: measured at 270x480,
+// three whole tiles + one half tile per SM take 92.5 us against 96.5 us for four whole ones).
+// p.tiles_x / p.nsplit = 1 set by the caller; sets p.nfull, p.nitems.
+static void choose_tiling(int out_h, int tiles_x, int G, Tc3Params &p) {
+    const int ntiles = tiles_x * ceil_div(out_h, 32);
+    p.nfull = ntiles;
+    p.nitems = ntiles;
+    const int urows = ceil_div(out_h, 16), units = urows * tiles_x;
+    const int q = units / (2 * G), nfull = q * G, nhalf = units - 2 * nfull;
+    const double mixed = 2.0 * q + 1.5 * ceil_div(nhalf, G), whole = 2.0 * ceil_div(ntiles, G);
+    if (q > 0 && nfull <= (urows / 2) * tiles_x && mixed < whole - 0.25) {
+        p.nfull = nfull;
+        p.nitems = nfull + nhalf;
+    }
+}
+
+// Introspection for the host-side tests (no GPU needed): the work items conv3x3_tc_kernel<2, *> would process for a
+// split-bf16 h x w layer on sm_count SMs, as (y0, x0, rows) triples in item order; returns the number of items.
+extern "C" int aivc_debug_tc3_tiling(int h, int w, int sm_count, int *tiles, int cap) {
+    Tc3Params p;
+    memset(&p, 0, sizeof(p));
+    p.tiles_x = ceil_div(w, TILE_W);
+    p.nsplit = 1;
+    p.ncta = 128;
+    choose_tiling(h, p.tiles_x, sm_count, p);
+    for (int i = 0; i < p.nitems && i < cap; ++i) {
+        int y0, x0, n0;
+        const int nsub = item_tile(p, i, 32, y0, x0, n0);
+        tiles[3 * i] = y0; tiles[3 * i + 1] = x0; tiles[3 * i + 2] = 16 * nsub;
+    }
+    return p.nitems;
+}
+
 // Returns -1 when the stage does not fit this kernel (caller falls through to the generic one).
 int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     const int cin = op->in.c, cout = op->out.c;
@@ -1152,20 +1187,7 @@ int conv_tc3_run(const aivc_conv_op *op, cudaStream_t st) {
     p.ncta = cout / p.nsplit;
     p.act = op->act; p.post = op->post;
     p.tiles_x = tiles_x; p.nitems = ntiles * p.nsplit; p.nfull = ntiles; p.in_pad = op->in.pad;
-    if (sub == 2 && x3 && !gdn) {
-        // whole tiles for as many full waves as the image holds, the rest as 16-row half tiles (item_tile) when that
-        // shortens the step.  Costs in half-tile units; a half tile is dearer than half a whole one (every weight
-        // group feeds half as many MMAs, so the two-deep group ring runs latency-bound: measured at 270x480, three
-        // whole tiles + one half tile per SM take 92.5 us against 96.5 us for four whole ones).
-        const int G = sm_count_cached();
-        const int urows = ceil_div(op->out.h, 16), units = urows * tiles_x;
-        const int q = units / (2 * G), nfull = q * G, nhalf = units - 2 * nfull;
-        const double mixed = 2.0 * q + 1.5 * ceil_div(nhalf, G), whole = 2.0 * ceil_div(ntiles, G);
-        if (q > 0 && nfull <= (urows / 2) * tiles_x && mixed < whole - 0.25) {
-            p.nfull = nfull;
-            p.nitems = nfull + nhalf;
-        }
-    }
+    if (sub == 2 && x3 && !gdn) choose_tiling(op->out.h, tiles_x, sm_count_cached(), p);
     p.b_bytes = (uint32_t)p.ncta * 128u;                       // weight rows one CTA stages per tap
     p.b_slot = (p.b_bytes + 1023u) & ~1023u;
     const size_t a_slot = sub == 1 ? Cfg<1>::A_SLOT : Cfg<2>::A_SLOT;

@@ -144,6 +144,10 @@ enum {
 };
 /* per kernel class k < n: out[3k] = ms, out[3k+1] = algorithmic flops, out[3k+2] = stages */
 int aivc_profile_read_classes(double *out, int n);
+/* Host-only introspection (tests): the work items the persistent 3x3 kernel processes for a split-bf16 h x w layer
+ * on sm_count SMs -- whole 32x8-pixel tiles for the full waves, 16-row half tiles for the rest -- as (y0, x0, rows)
+ * triples in item order (at most cap of them are written); returns the number of items.  No reference counterpart. */
+int aivc_debug_tc3_tiling(int h, int w, int sm_count, int *tiles, int cap);
 
 /* ---- convolution stack ------------------------------------------------------------- */
 /* Re-layout a PyTorch weight for an engine.  src: Conv2d [cout][cin][k][k] or

@@ -251,3 +251,37 @@ def test_codec_cache_is_versioned_weak_and_bounded(monkeypatch):
     del net, a, b
     gc.collect()
     assert len(adapter._CODECS) == n - 1
+
+
+@pytest.mark.parametrize('size', [(270, 480), (272, 480), (270, 481), (540, 960), (544, 960), (360, 640), (1080, 1920),
+                                  (300, 1000), (33, 47), (600, 808)])
+@pytest.mark.parametrize('sms', [148, 132, 7])
+def test_persistent_3x3_tiling_covers_the_image_exactly_once(size, sms):
+    """Host-side check of the work-item cut of the persistent split-bf16 3x3 kernel (csrc/conv_tc3.cu::choose_tiling +
+    item_tile, the same function the device code runs): whole 32x8 tiles and 16-row half tiles together cover every
+    pixel of the layer exactly once, the whole tiles fill complete waves when half tiles are used, and a mixed cut
+    is only chosen where its estimated cost is below that of whole tiles."""
+    h, w = size
+    L = _lib.lib()
+    cap = 1 << 16
+    buf = np.zeros((cap, 3), dtype=np.int32)
+    n = L.aivc_debug_tc3_tiling(h, w, sms, buf.ctypes.data_as(C.c_void_p), cap)
+    assert 0 < n <= cap
+    t = buf[:n]
+    cover = np.zeros((h + 64, w + 16), dtype=np.int32)
+    for y0, x0, rows in t:
+        assert rows in (16, 32) and x0 % 8 == 0 and y0 % 16 == 0
+        cover[y0:y0 + rows, x0:x0 + 8] += 1
+    assert (cover[:h, :w] == 1).all(), 'every pixel exactly once'
+    assert cover.max() == 1, 'no tile overlaps another, inside or outside the image'
+    nfull, nhalf = int((t[:, 2] == 32).sum()), int((t[:, 2] == 16).sum())
+    assert (t[:nfull, 2] == 32).all(), 'whole tiles first'
+    whole_only = -(-w // 8) * -(-h // 32)
+    if nhalf:
+        assert nfull % sms == 0
+        # cost model of choose_tiling: a half tile counts 0.75 of a whole one
+        assert 2.0 * (nfull // sms) + 1.5 * -(-nhalf // sms) < 2.0 * -(-whole_only // sms)
+    else:
+        assert n == whole_only
+    if size in ((270, 480), (272, 480)) and sms == 148:
+        assert (nfull, nhalf) == (444, 132)
